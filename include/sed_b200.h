@@ -1,0 +1,101 @@
+/* sed_b200.h -- C ABI of libsedb200.so: the B200 (sm_100a) kernels behind the reference's
+ * per-clip training path.
+ *
+ * Boundary rules:
+ *  - plain pointers + sizes + an explicit cudaStream_t (passed as void*); no torch types.
+ *  - every tensor (inputs, outputs, saved-for-backward, workspaces) is allocated by the caller
+ *    (PyTorch's caching allocator on the Python side) and only BORROWED for the duration of the
+ *    enqueue; the library never allocates or frees device memory, never synchronises, never
+ *    changes the current device.
+ *  - every entry point returns 0 on success and a non-zero status otherwise; the message is
+ *    retrievable (per thread) with sed_last_error_string().  No C++ exceptions cross the ABI.
+ *  - entry points are re-entrant and thread-safe (DataParallel calls forward from one Python
+ *    thread per GPU; autograd runs backward on per-device worker threads).
+ *  - there is NO CPU fallback inside the library.
+ *
+ * Each entry point cites the reference interface it replaces, relative to /root/reference.
+ * Layouts: activations are NHWC ("pixels x channels", H = time frames, W = mel/freq bins),
+ * bf16 unless stated; weights for the tensor-core convolutions are repacked bf16 shadows of the
+ * reference's OIHW fp32 master copies.
+ */
+#ifndef SED_B200_H_
+#define SED_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* sed_stream_t; /* a cudaStream_t */
+
+/* ---- library ------------------------------------------------------------------------------ */
+const char* sed_last_error_string(void);
+int sed_abi_version(void);
+/* Number of kernels this library has launched on any stream since load (thread-safe counter);
+ * bench.py reports the delta over the timed region as "gpu_launches". */
+unsigned long long sed_launch_count(void);
+int sed_device_sm_count(int* out_sms);
+
+/* ---- front-end: torchlibrosa.stft.Spectrogram + LogmelFilterBank ---------------------------
+ * replaces pytorch/models.py:199-200 (Spectrogram.forward -> LogmelFilterBank.forward) and the
+ * six sibling call sites; ctor contracts pytorch/models.py:166-173.
+ * n_fft is fixed at 1024 (utils/config.py:11); window = periodic Hann; center=True, reflect pad.
+ *
+ * Mel bank in CSR-by-mel form (built on the host from the module's frozen melW parameter):
+ *   mel_lo[m]   first FFT bin with a non-zero tap,  mel_off[m]..mel_off[m+1] its taps in mel_w.
+ * out = 10*log10(max(mel, amin)) - db_offset,  db_offset = 10*log10(max(amin, ref)).
+ */
+int sed_logmel_f32(const float* wave, int n_clips, int n_samples, int hop,
+                   const float* mel_w, const int* mel_lo, const int* mel_off, int n_mels,
+                   float amin, float db_offset, float* out /* (n_clips, T, n_mels) */,
+                   sed_stream_t stream);
+/* Same with int16 PCM input; x/32767 (utils/utilities.py:66-67) is fused into the frame gather. */
+int sed_logmel_i16(const int16_t* pcm, int n_clips, int n_samples, int hop,
+                   const float* mel_w, const int* mel_lo, const int* mel_off, int n_mels,
+                   float amin, float db_offset, float* out, sed_stream_t stream);
+/* Unfused seam A: Spectrogram.forward alone -> (n_clips, T, 513) power spectrogram. */
+int sed_stft_power_f32(const float* wave, int n_clips, int n_samples, int hop,
+                       float* out_power, sed_stream_t stream);
+/* Unfused seam A: LogmelFilterBank.forward alone on a (rows, 513) power spectrogram. */
+int sed_mel_db_f32(const float* power, long long rows, int n_bins,
+                   const float* mel_w, const int* mel_lo, const int* mel_off, int n_mels,
+                   float amin, float db_offset, int is_log, float* out, sed_stream_t stream);
+
+
+/* ---- 3x3 convolutions on tensor cores (tcgen05 + TMA) --------------------------------------
+ * replaces the cuDNN calls behind ConvBlock.conv1 / conv2 (pytorch/models.py:75-83, :102-103)
+ * and their autograd backward (pytorch/main.py:257).  Activations NHWC bf16 [B][H][W][C]
+ * (H = frames, W = mel bins); 128 % W == 0, W >= 8; Cin % 64 == 0.
+ */
+/* fp32 OIHW master weights -> bf16 shadows: fwd [Cout][tap][Cin]; dgrad [Cin][8-tap][Cout]. */
+int sed_conv_pack_weights(const float* w_oihw, int Cout, int Cin, void* fwd_pack, void* dgrad_pack,
+                          sed_stream_t stream);
+/* grid size the conv kernel will use = number of rows of the stats_partial workspace. */
+int sed_conv3x3_tc_grid(int B, int H, int W, int Cout);
+/* y = conv3x3(x, w) (bf16 out, fp32 accumulate).  stats_partial (optional):
+ * [sed_conv3x3_tc_grid()][2][Cout] per-CTA (sum, sum of squares) of the fp32 results, for the
+ * training-mode BatchNorm that follows.  The data gradient is the same call with
+ * x = dY, wpack = the dgrad pack and Cin/Cout swapped. */
+int sed_conv3x3_tc_fwd(const void* x, const void* wpack, void* y, float* stats_partial, int B, int H,
+                       int W, int Cin, int Cout, sed_stream_t stream);
+/* weight gradient: slabs = [sed_conv3x3_tc_wgrad_splits()][9][Cout][Cin] fp32 split-K partials;
+ * sed_conv_unpack_wgrad sums them (fixed order) into the OIHW fp32 gradient. */
+int sed_conv3x3_tc_wgrad_splits(int B, int H, int W, int Cin, int Cout);
+int sed_conv3x3_tc_wgrad(const void* dy, const void* x, float* slabs, int B, int H, int W, int Cin,
+                         int Cout, sed_stream_t stream);
+int sed_conv_unpack_wgrad(const float* g_tap_major, int slabs, long long slab_stride, int Cout, int Cin,
+                          float* grad_oihw, int accumulate, sed_stream_t stream);
+int sed_f32_to_bf16(const float* x, void* y, long long n, sed_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#endif /* SED_B200_H_ */

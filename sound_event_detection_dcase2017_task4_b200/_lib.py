@@ -1,0 +1,83 @@
+"""ctypes binding of libsedb200.so (the C ABI in include/sed_b200.h).
+
+ctypes releases the GIL for the duration of every call, so DataParallel's per-GPU Python
+threads enqueue concurrently.  All functions return an int status; ``call`` turns a non-zero
+status into ``RuntimeError(sed_last_error_string())``.
+"""
+import ctypes
+import os
+import threading
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, 'libsedb200.so')
+
+_c_int, _c_ll, _c_float, _c_void_p = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_void_p
+P, I, L, F = _c_void_p, _c_int, _c_ll, _c_float
+
+# name -> argtypes (all return int unless listed in _RESTYPES)
+SIGNATURES = {
+    'sed_abi_version': [],
+    'sed_launch_count': [],
+    'sed_last_error_string': [],
+    'sed_device_sm_count': [P],
+    'sed_logmel_f32': [P, I, I, I, P, P, P, I, F, F, P, P],
+    'sed_logmel_i16': [P, I, I, I, P, P, P, I, F, F, P, P],
+    'sed_stft_power_f32': [P, I, I, I, P, P],
+    'sed_mel_db_f32': [P, L, I, P, P, P, I, F, F, I, P, P],
+    'sed_conv_pack_weights': [P, I, I, P, P, P],
+    'sed_conv3x3_tc_grid': [I, I, I, I],
+    'sed_conv3x3_tc_fwd': [P, P, P, P, I, I, I, I, I, P],
+    'sed_conv3x3_tc_wgrad_splits': [I, I, I, I, I],
+    'sed_conv3x3_tc_wgrad': [P, P, P, I, I, I, I, I, P],
+    'sed_conv_unpack_wgrad': [P, I, L, I, I, P, I, P],
+    'sed_f32_to_bf16': [P, P, L, P],
+}
+_RESTYPES = {
+    'sed_last_error_string': ctypes.c_char_p,
+    'sed_launch_count': ctypes.c_ulonglong,
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def lib():
+    """The loaded library.  Raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        'libsedb200.so is missing (%s). Build it with '
+                        '`python -m sound_event_detection_dcase2017_task4_b200.build`; '
+                        'there is no CPU / PyTorch fallback for this path.' % LIB_PATH)
+                handle = ctypes.CDLL(LIB_PATH)
+                for name, argtypes in SIGNATURES.items():
+                    fn = getattr(handle, name)          # AttributeError = ABI drift: fail loudly
+                    fn.argtypes = argtypes
+                    fn.restype = _RESTYPES.get(name, ctypes.c_int)
+                _lib = handle
+    return _lib
+
+
+def call(name, *args):
+    fn = getattr(lib(), name)
+    status = fn(*args)
+    if status != 0:
+        msg = lib().sed_last_error_string()
+        raise RuntimeError('%s failed (status %d): %s' % (name, status, (msg or b'').decode()))
+
+
+def launch_count():
+    return int(lib().sed_launch_count())
+
+
+def ptr(t):
+    """Device pointer of a tensor (0 for None)."""
+    return 0 if t is None else t.data_ptr()
+
+
+def stream_of(t):
+    import torch
+    return torch.cuda.current_stream(t.device).cuda_stream

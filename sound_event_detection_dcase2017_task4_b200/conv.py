@@ -1,0 +1,67 @@
+"""Launch wrappers for the tensor-core 3x3 convolution family (csrc/conv_tc.cu,
+csrc/conv_wgrad_tc.cu, csrc/pack.cu).  Tensors are NHWC bf16 (B, H, W, C)."""
+import torch
+
+from . import _lib
+
+
+def tc_supported(W, Cin, Cout):
+    return (W >= 8 and W <= 128 and 128 % W == 0 and Cin >= 64 and Cin % 64 == 0 and
+            (Cin == 64 or Cin % 128 == 0) and (Cout in (64, 128, 256, 512)))
+
+
+def pack_weights(w_oihw, want_fwd=True, want_dgrad=True):
+    """fp32 (Cout, Cin, 3, 3) -> (fwd bf16 [Cout, 9*Cin], dgrad bf16 [Cin, 9*Cout])."""
+    assert w_oihw.is_cuda and w_oihw.dtype == torch.float32 and tuple(w_oihw.shape[2:]) == (3, 3)
+    w = w_oihw.detach().contiguous()
+    cout, cin = w.shape[:2]
+    fwd = torch.empty((cout, 9 * cin), dtype=torch.bfloat16, device=w.device) if want_fwd else None
+    dg = torch.empty((cin, 9 * cout), dtype=torch.bfloat16, device=w.device) if want_dgrad else None
+    with torch.cuda.device(w.device):
+        _lib.call('sed_conv_pack_weights', w.data_ptr(), cout, cin, _lib.ptr(fwd), _lib.ptr(dg),
+                  _lib.stream_of(w))
+    return fwd, dg
+
+
+def conv3x3(x, wpack, cout, want_stats=False):
+    """x (B,H,W,Cin) bf16, wpack [cout, 9*Cin] bf16 -> y (B,H,W,cout) bf16
+    [, stats_partial (grid, 2, cout) fp32]."""
+    assert x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous()
+    b, h, w, cin = x.shape
+    assert wpack.shape == (cout, 9 * cin) and wpack.dtype == torch.bfloat16 and wpack.is_contiguous()
+    y = torch.empty((b, h, w, cout), dtype=torch.bfloat16, device=x.device)
+    stats = None
+    with torch.cuda.device(x.device):
+        if want_stats:
+            grid = _lib.lib().sed_conv3x3_tc_grid(b, h, w, cout)
+            stats = torch.empty((grid, 2, cout), dtype=torch.float32, device=x.device)
+        _lib.call('sed_conv3x3_tc_fwd', x.data_ptr(), wpack.data_ptr(), y.data_ptr(), _lib.ptr(stats),
+                  b, h, w, cin, cout, _lib.stream_of(x))
+    return (y, stats) if want_stats else y
+
+
+def conv3x3_wgrad(dy, x, out=None, accumulate=False):
+    """dy (B,H,W,Cout) bf16, x (B,H,W,Cin) bf16 -> dW fp32 (Cout, Cin, 3, 3)."""
+    assert dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16
+    assert dy.is_contiguous() and x.is_contiguous() and dy.shape[:3] == x.shape[:3]
+    b, h, w, cin = x.shape
+    cout = dy.shape[3]
+    with torch.cuda.device(x.device):
+        splits = _lib.lib().sed_conv3x3_tc_wgrad_splits(b, h, w, cin, cout)
+        slabs = torch.empty((splits, 9, cout, cin), dtype=torch.float32, device=x.device)
+        _lib.call('sed_conv3x3_tc_wgrad', dy.data_ptr(), x.data_ptr(), slabs.data_ptr(), b, h, w, cin,
+                  cout, _lib.stream_of(x))
+        if out is None:
+            out = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=x.device)
+            accumulate = False
+        _lib.call('sed_conv_unpack_wgrad', slabs.data_ptr(), splits, 9 * cout * cin, cout, cin,
+                  out.data_ptr(), 1 if accumulate else 0, _lib.stream_of(x))
+    return out
+
+
+def to_bf16(x):
+    x = x.contiguous()
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call('sed_f32_to_bf16', x.data_ptr(), y.data_ptr(), x.numel(), _lib.stream_of(x))
+    return y

@@ -1,0 +1,75 @@
+// common.cuh -- shared host/device helpers for libsedb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/sed_b200.h"
+
+namespace sed {
+
+// ---- error plumbing (no exceptions across the C ABI) --------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define SED_REQUIRE(cond, ...)            \
+  do {                                    \
+    if (!(cond)) {                        \
+      ::sed::set_error(__VA_ARGS__);      \
+      return 1;                           \
+    }                                     \
+  } while (0)
+
+#define SED_CUDA(expr)                                                                  \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      ::sed::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                       __LINE__);                                                       \
+      return 2;                                                                         \
+    }                                                                                   \
+  } while (0)
+
+// call right after a <<<>>> launch
+#define SED_LAUNCH_CHECK(name)                                                        \
+  do {                                                                                \
+    cudaError_t _e = cudaGetLastError();                                              \
+    if (_e != cudaSuccess) {                                                          \
+      ::sed::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));      \
+      return 3;                                                                       \
+    }                                                                                 \
+    ::sed::count_launch();                                                            \
+  } while (0)
+
+inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+int sm_count();   // of the current device (cached per device)
+
+// ---- device helpers ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
+  __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&v);
+  return __bfloat1622float2(t);
+}
+__device__ __forceinline__ float bf16_bits_to_float(uint16_t b) {
+  return __uint_as_float(((uint32_t)b) << 16);
+}
+#endif
+
+}  // namespace sed

@@ -1,0 +1,290 @@
+// conv_tc.cu -- 3x3 / stride 1 / pad 1 convolution as a tcgen05 implicit GEMM (sm_100a).
+//
+// Replaces the cuDNN calls behind ConvBlock.conv1/conv2 (/root/reference/pytorch/models.py:75-83,
+// forward :102-103) for every layer with Cin % 64 == 0, and -- with the rotated / transposed
+// weight pack -- their data-gradient.
+//
+//   D[M = 128 pixels][N = Cout tile] = sum over 9 taps x (Cin/64) K-blocks  A_tap[128][64] * W_tap[N][64]^T
+//
+// * activations are NHWC bf16; an M tile is a (bh x W) rectangle of output pixels of one clip,
+//   bh*W = 128.  For tap (kh,kw) the A operand is the same rectangle shifted by (kh-1, kw-1):
+//   ONE 4-D TMA box {64 ch, W, bh, 1} at coordinates {c0, kw-1, h0+kh-1, b}.  Out-of-range
+//   coordinates are zero-filled by the TMA unit, which IS the conv's zero padding (and the H
+//   tail), so the im2col matrix never exists anywhere -- not in HBM, not in shared memory.
+// * weights are a bf16 [Cout][9*Cin] K-major matrix (k = tap*Cin + ci): 2-D TMA box {64, N}.
+// * both land in 128B-swizzled K-major shared-memory tiles that tcgen05.mma consumes directly;
+//   fp32 accumulators live in TMEM (double buffered: the epilogue of tile i overlaps the MMAs
+//   of tile i+1).
+// * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2-5 = epilogue:
+//   tcgen05.ld -> bf16 NHWC store, and per-channel sum / sum-of-squares of the fp32
+//   accumulators for the training-mode BatchNorm that follows (warp-transpose reduction,
+//   accumulated per CTA in shared memory, flushed once: deterministic two-level reduction).
+// * persistent: grid = min(#tiles, #SMs), static round-robin tile schedule.
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace sed {
+namespace {
+
+using namespace tc;
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                       // bf16 elements = one 128 B swizzle row
+constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
+constexpr int kNumThreads = 192;                  // 6 warps
+constexpr int kEpiThreads = 128;
+
+template <int kN> struct Cfg {
+  static constexpr int kBBytes = kN * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (kN == 256) ? 4 : (kN == 128 ? 6 : 8);
+  static constexpr uint32_t kTmemCols = (2 * kN <= 32) ? 32 : (2 * kN <= 64) ? 64 : (2 * kN <= 128) ? 128 : (2 * kN <= 256) ? 256 : 512;
+  static constexpr int kDynSmem = kStages * kStageBytes + 1024;   // +1024 for manual alignment
+};
+
+struct ConvParams {
+  int B, H, W, Cin, Cout;
+  int bh;            // tile height in pixels; bh * W == 128
+  int tiles_h;       // ceil(H / bh)
+  int tiles_n;       // Cout / kN
+  int num_tiles;     // B * tiles_h * tiles_n
+  int kb_per_tap;    // Cin / 64
+  __nv_bfloat16* y;  // NHWC output
+  float* stats;      // [gridDim.x][2][Cout] partial (sum, sumsq) or nullptr
+};
+
+template <int kN>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const ConvParams p) {
+  using C = Cfg<kN>;
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle needs 1024 B aligned tiles
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[C::kStages], empty_bar[C::kStages], tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_stats[2 * 512];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = 9 * p.kb_per_tap;
+
+  for (int i = threadIdx.x; i < 2 * p.Cout; i += kNumThreads) s_stats[i] = 0.f;
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], kEpiThreads);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<C::kTmemCols>(&tmem_base_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.tiles_n;
+        const int m_tile = tile / p.tiles_n;
+        const int b = m_tile / p.tiles_h;
+        const int h0 = (m_tile % p.tiles_h) * p.bh;
+        for (int tap = 0; tap < 9; ++tap) {
+          const int kh = tap / 3, kw = tap % 3;
+          for (int cb = 0; cb < p.kb_per_tap; ++cb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * C::kStageBytes;
+            uint8_t* sb = sa + kABytes;
+            mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
+            tma_load_4d(sa, &tmap_a, &full_bar[stage], cb * kBlockK, kw - 1, h0 + kh - 1, b);
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], tap * p.Cin + cb * kBlockK, n_tile * kN);
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, kN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+          const uint32_t sb = sa + kABytes;
+#pragma unroll
+          for (int ks = 0; ks < kBlockK / 16; ++ks) {
+            const uint64_t da = umma_desc_sw128(sa + ks * 32, 16, 1024);
+            const uint64_t db = umma_desc_sw128(sb + ks * 32, 16, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (kb | ks) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);          // smem slot reusable once these MMAs retire
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full_bar[acc]);          // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int r_h = row / p.W, r_w = row % p.W;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int n_tile = tile % p.tiles_n;
+      const int m_tile = tile / p.tiles_n;
+      const int b = m_tile / p.tiles_h;
+      const int h = (m_tile % p.tiles_h) * p.bh + r_h;
+      const bool valid = h < p.H;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      __nv_bfloat16* dst = p.y + (((long long)b * p.H + h) * p.W + r_w) * p.Cout + n_tile * kN;
+#pragma unroll 1
+      for (int c = 0; c < kN / 32; ++c) {
+        float v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kN + c * 32, v);
+        if (valid) {
+          uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 o;
+            o.x = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]);
+            o.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
+            o.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
+            o.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
+            d4[g] = o;
+          }
+        }
+        if (p.stats != nullptr) {
+          float sq[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            v[i] = valid ? v[i] : 0.f;
+            sq[i] = v[i] * v[i];
+          }
+          // warp transpose-reduce: afterwards lane l holds the column-(l) total over the 32 rows
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool hi = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+              const float send = hi ? v[i] : v[i + off];
+              const float keep = hi ? v[i + off] : v[i];
+              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+              const float send2 = hi ? sq[i] : sq[i + off];
+              const float keep2 = hi ? sq[i + off] : sq[i];
+              sq[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+            }
+          }
+          const int ch = n_tile * kN + c * 32 + lane;
+          atomicAdd(&s_stats[ch], v[0]);
+          atomicAdd(&s_stats[p.Cout + ch], sq[0]);
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);
+    }
+    if (p.stats != nullptr) {
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      float* out = p.stats + (long long)blockIdx.x * 2 * p.Cout;
+      for (int i = threadIdx.x - 64; i < 2 * p.Cout; i += kEpiThreads) out[i] = s_stats[i];
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
+}
+
+template <int kN>
+int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, int grid, cudaStream_t stream) {
+  auto kern = conv3x3_tc_kernel<kN>;
+  SED_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<kN>::kDynSmem));
+  kern<<<grid, kNumThreads, Cfg<kN>::kDynSmem, stream>>>(ta, tb, p);
+  SED_LAUNCH_CHECK("conv3x3_tc_kernel");
+  return 0;
+}
+
+}  // namespace
+}  // namespace sed
+
+using namespace sed;
+
+extern "C" {
+
+int sed_conv3x3_tc_grid(int B, int H, int W, int Cout) {
+  if (W <= 0 || 128 % W != 0) return 0;
+  const int bh = 128 / W;
+  const int kN = Cout >= 256 ? 256 : Cout;
+  if (kN <= 0 || Cout % kN != 0) return 0;
+  const long long tiles = (long long)B * ((H + bh - 1) / bh) * (Cout / kN);
+  return (int)(tiles < sm_count() ? tiles : sm_count());
+}
+
+int sed_conv3x3_tc_fwd(const void* x, const void* wpack, void* y, float* stats_partial, int B, int H, int W,
+                       int Cin, int Cout, sed_stream_t stream) {
+  SED_REQUIRE(x && wpack && y, "sed_conv3x3_tc_fwd: null pointer");
+  SED_REQUIRE(B > 0 && H > 0, "sed_conv3x3_tc_fwd: empty batch");
+  SED_REQUIRE(W >= 8 && W <= 128 && 128 % W == 0, "sed_conv3x3_tc_fwd: W=%d must divide 128 and be >= 8", W);
+  SED_REQUIRE(Cin % 64 == 0 && Cin >= 64, "sed_conv3x3_tc_fwd: Cin=%d must be a multiple of 64", Cin);
+  SED_REQUIRE(Cout == 64 || Cout == 128 || Cout % 256 == 0, "sed_conv3x3_tc_fwd: Cout=%d unsupported", Cout);
+  SED_REQUIRE(Cout <= 512, "sed_conv3x3_tc_fwd: Cout=%d > 512", Cout);
+  SED_REQUIRE(aligned(y, 16), "sed_conv3x3_tc_fwd: output must be 16-byte aligned");
+  const int kN = Cout >= 256 ? 256 : Cout;
+  ConvParams p;
+  p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  p.bh = 128 / W;
+  p.tiles_h = (H + p.bh - 1) / p.bh;
+  p.tiles_n = Cout / kN;
+  p.num_tiles = B * p.tiles_h * p.tiles_n;
+  p.kb_per_tap = Cin / 64;
+  p.y = reinterpret_cast<__nv_bfloat16*>(y);
+  p.stats = stats_partial;
+  const int grid = sed_conv3x3_tc_grid(B, H, W, Cout);
+
+  alignas(64) CUtensorMap ta, tb;
+  {
+    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    const uint32_t box[4] = {64, (uint32_t)W, (uint32_t)p.bh, 1};
+    if (int rc = tc::make_tmap_bf16(&ta, x, 4, dims, strides, box, "conv activation map")) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)9 * Cin, (uint64_t)Cout};
+    const uint64_t strides[1] = {(uint64_t)9 * Cin * 2};
+    const uint32_t box[2] = {64, (uint32_t)kN};
+    if (int rc = tc::make_tmap_bf16(&tb, wpack, 2, dims, strides, box, "conv weight map")) return rc;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (kN) {
+    case 64: return launch_conv<64>(ta, tb, p, grid, s);
+    case 128: return launch_conv<128>(ta, tb, p, grid, s);
+    case 256: return launch_conv<256>(ta, tb, p, grid, s);
+  }
+  SED_REQUIRE(false, "sed_conv3x3_tc_fwd: no kernel for N tile %d", kN);
+}
+
+}  // extern "C"

@@ -1,0 +1,68 @@
+"""-m gpu: tcgen05 implicit-GEMM 3x3 convolution (fwd, dgrad, wgrad, BN statistics) through the
+C ABI against a plain PyTorch fp32 reference evaluated on the same bf16-rounded operands.
+Tolerance: the kernel accumulates in fp32 and rounds once to bf16 (rel 2^-9 = 1.95e-3)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [  # (B, H, W, Cin, Cout)
+    (2, 101, 64, 64, 64),      # block1.conv2 on a 1 s clip (H tail: 101 = 50*2 + 1)
+    (3, 50, 32, 64, 128),      # block2.conv1
+    (2, 50, 32, 128, 128),     # block2.conv2
+    (2, 25, 16, 128, 256),     # block3.conv1 (H tail 25 = 3*8 + 1)
+    (2, 25, 16, 256, 256),     # block3.conv2
+    (2, 12, 8, 256, 512),      # block4.conv1 (two N tiles, H tail)
+    (1, 125, 8, 512, 512),     # block4.conv2 at the full 10 s length
+    (150, 4, 32, 64, 128),     # more tiles than SMs: persistent loop + accumulator double buffering
+]
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale)
+
+
+@pytest.mark.parametrize('B,H,W,Cin,Cout', SHAPES)
+def test_conv_fwd_and_stats(B, H, W, Cin, Cout):
+    from sound_event_detection_dcase2017_task4_b200 import conv
+    x = _rand((B, H, W, Cin), 1).cuda().to(torch.bfloat16)
+    w = (_rand((Cout, Cin, 3, 3), 2) * (2.0 / (9 * Cin)) ** 0.5).cuda()
+    wf, _ = conv.pack_weights(w)
+    y, stats = conv.conv3x3(x, wf, Cout, want_stats=True)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), padding=1).permute(0, 2, 3, 1)
+    err = (y.float() - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item() + 1e-3, err
+    s = stats.double().sum(dim=0)                 # (2, Cout)
+    n = B * H * W
+    mean_ref = ref.double().mean(dim=(0, 1, 2))
+    sq_ref = (ref.double() ** 2).mean(dim=(0, 1, 2))
+    assert torch.allclose(s[0] / n, mean_ref, atol=1e-4, rtol=1e-4)
+    assert torch.allclose(s[1] / n, sq_ref, atol=1e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize('B,H,W,Cin,Cout', SHAPES)
+def test_conv_dgrad(B, H, W, Cin, Cout):
+    from sound_event_detection_dcase2017_task4_b200 import conv
+    dy = _rand((B, H, W, Cout), 3).cuda().to(torch.bfloat16)
+    w = (_rand((Cout, Cin, 3, 3), 4) * (2.0 / (9 * Cout)) ** 0.5).cuda()
+    _, wd = conv.pack_weights(w)
+    dx = conv.conv3x3(dy, wd, Cin)
+    ref = F.conv_transpose2d(dy.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), padding=1).permute(0, 2, 3, 1)
+    err = (dx.float() - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item() + 1e-3, err
+
+
+@pytest.mark.parametrize('B,H,W,Cin,Cout', SHAPES)
+def test_conv_wgrad(B, H, W, Cin, Cout):
+    from sound_event_detection_dcase2017_task4_b200 import conv
+    x = _rand((B, H, W, Cin), 5).cuda().to(torch.bfloat16)
+    dy = _rand((B, H, W, Cout), 6).cuda().to(torch.bfloat16)
+    dw = conv.conv3x3_wgrad(dy, x)
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(False)
+    wr = torch.zeros((Cout, Cin, 3, 3), device='cuda', requires_grad=True)
+    F.conv2d(xr, wr, padding=1).backward(dy.float().permute(0, 3, 1, 2))
+    ref = wr.grad
+    err = (dw - ref).abs().max().item()
+    assert err <= 1e-3 * ref.abs().max().item() + 1e-3, err
