@@ -92,6 +92,76 @@ int sed_conv_unpack_wgrad(const float* g_tap_major, int slabs, long long slab_st
                           float* grad_oihw, int accumulate, sed_stream_t stream);
 int sed_f32_to_bf16(const float* x, void* y, long long n, sed_stream_t stream);
 
+
+/* ---- BatchNorm2d(train) + ReLU + avg-pool on NHWC bf16 ---------------------------------------
+ * replaces F.relu_(self.bnX(...)) + F.avg_pool2d (pytorch/models.py:102-113) and, with
+ * (ph, pw) = (1, W), block 4's identity pool + torch.mean(x, dim=3) (models.py:303 and siblings).
+ * partial = [P][2][C] per-CTA (sum, sum of squares) rows written by the producing conv kernel. */
+int sed_bn_finalize(const float* partial, int P, int C, double count, const float* gamma, const float* beta,
+                    float eps, float momentum, float* running_mean, float* running_var,
+                    long long* num_batches_tracked, float* scale, float* shift, float* save_mean,
+                    float* save_invstd, sed_stream_t stream);
+int sed_bn_eval_affine(const float* running_mean, const float* running_var, const float* gamma, const float* beta,
+                       float eps, int C, float* scale, float* shift, sed_stream_t stream);
+int sed_bn_relu_pool_fwd(const void* y, const float* scale, const float* shift, int B, int H, int W, int C, int ph,
+                         int pw, void* out, int out_is_f32, sed_stream_t stream);
+int sed_bn_bwd_partials(int C);
+int sed_bn_relu_pool_bwd_reduce(const void* y, const void* dA, int grad_is_f32, const float* scale,
+                                const float* shift, const float* mean, const float* invstd, int B, int H, int W,
+                                int C, int ph, int pw, float* partial, sed_stream_t stream);
+int sed_bn_bwd_finalize(const float* partial, int P, int C, double count, const float* gamma, const float* invstd,
+                        float* dgamma, float* dbeta, int accumulate, float* coef, sed_stream_t stream);
+int sed_bn_relu_pool_bwd_apply(const void* y, const void* dA, int grad_is_f32, const float* scale, const float* shift,
+                               const float* mean, const float* invstd, const float* coef, int B, int H, int W, int C,
+                               int ph, int pw, void* dy, sed_stream_t stream);
+
+/* ---- bn0 + SpecAugment + mixup (pytorch/models.py:202-211, pytorch_utils.py:80-93) ------------
+ * stripes: int32 (B2, n, 2) = (begin, width), drawn on the host in torchlibrosa's RNG order. */
+int sed_stat_partials(void);
+int sed_colstats_f32(const float* x, long long rows, int C, float* partial, sed_stream_t stream);
+int sed_bn0_aug_mix_fwd(const float* logmel, const float* scale, const float* shift, const int* t_stripes, int nt,
+                        const int* f_stripes, int nf, const float* lam, int B2, int T, int M, float* out,
+                        sed_stream_t stream);
+int sed_bn0_bwd_reduce(const float* dout, const float* logmel, const float* mean, const float* invstd,
+                       const int* t_stripes, int nt, const int* f_stripes, int nf, const float* lam, int B2, int T,
+                       int M, float* partial, sed_stream_t stream);
+/* torchlibrosa.augmentation.SpecAugmentation.forward stand-alone (in place, (B,C,T,F) fp32). */
+int sed_spec_augment_f32(float* x, int B, int C, int T, int F, const int* t_stripes, int nt, const int* f_stripes,
+                         int nf, sed_stream_t stream);
+int sed_reduce_partials(const float* partial, int P, long long n, float* out, int accumulate, float scale,
+                        sed_stream_t stream);
+
+/* ---- first convolution, Cin = 1 (ConvBlock1.conv1, pytorch/models.py:181, :102) -------------- */
+int sed_conv_c1_grid(void);
+int sed_conv_c1_fwd(const float* x, const float* w, void* y, float* stats_partial, int B, int H, int W, int Cout,
+                    sed_stream_t stream);
+int sed_conv_c1_wgrad(const float* x, const void* dy, float* partial, int B, int H, int W, int Cout,
+                      sed_stream_t stream);
+int sed_conv_c1_dgrad(const void* dy, const float* w, float* dx, int B, int H, int W, int Cout, sed_stream_t stream);
+
+/* ---- heads + loss (pytorch/models.py:118-149, :221-227, :306-312; pytorch/losses.py:5-12) ------ */
+int sed_linear_partials(void);
+int sed_linear_small_fwd(const float* x, const float* W, const float* bias, long long R, int C, int K, float* out,
+                         sed_stream_t stream);
+int sed_linear_small_bwd(const float* dout, const float* x, const float* W, long long R, int C, int K, float* dx,
+                         float* partial_w, float* partial_b, sed_stream_t stream);
+int sed_head_pool_fwd(const float* logit, int B, int T, int K, int ratio, int mode, float* prob, float* clip,
+                      int* argmax, float* frame, sed_stream_t stream);
+int sed_head_pool_bwd(const float* prob, const float* dclip, const int* argmax, int B, int T, int K, int mode,
+                      float* dlogit, sed_stream_t stream);
+int sed_head_att_fwd(const float* att_logit, const float* cla_logit, int B, int T, int K, int ratio, int sigmoid_act,
+                     float temperature, float* norm_att, float* cla, float* clip, float* frame, sed_stream_t stream);
+int sed_head_att_bwd(const float* att_logit, const float* norm_att, const float* cla, const float* clip,
+                     const float* dclip, int B, int T, int K, int sigmoid_act, float temperature, float* d_att_logit,
+                     float* d_cla_logit, sed_stream_t stream);
+int sed_bce_fwd_bwd(const float* prob, const float* target, long long n, float grad_scale, float* loss, float* dprob,
+                    sed_stream_t stream);
+
+/* ---- optimizer: optim.Adam(amsgrad=True).step() (pytorch/main.py:144-145, :258) ---------------- */
+int sed_adam_amsgrad(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq,
+                     long long n, float lr, float beta1, float beta2, float eps, int step, float grad_scale,
+                     sed_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

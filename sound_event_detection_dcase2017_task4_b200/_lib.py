@@ -12,7 +12,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, 'libsedb200.so')
 
 _c_int, _c_ll, _c_float, _c_void_p = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_void_p
-P, I, L, F = _c_void_p, _c_int, _c_ll, _c_float
+P, I, L, F, D = _c_void_p, _c_int, _c_ll, _c_float, ctypes.c_double
 
 # name -> argtypes (all return int unless listed in _RESTYPES)
 SIGNATURES = {
@@ -31,6 +31,32 @@ SIGNATURES = {
     'sed_conv3x3_tc_wgrad': [P, P, P, I, I, I, I, I, P],
     'sed_conv_unpack_wgrad': [P, I, L, I, I, P, I, P],
     'sed_f32_to_bf16': [P, P, L, P],
+    'sed_bn_finalize': [P, I, I, D, P, P, F, F, P, P, P, P, P, P, P, P],
+    'sed_bn_eval_affine': [P, P, P, P, F, I, P, P, P],
+    'sed_bn_relu_pool_fwd': [P, P, P, I, I, I, I, I, I, P, I, P],
+    'sed_bn_bwd_partials': [I],
+    'sed_bn_relu_pool_bwd_reduce': [P, P, I, P, P, P, P, I, I, I, I, I, I, P, P],
+    'sed_bn_bwd_finalize': [P, I, I, D, P, P, P, P, I, P, P],
+    'sed_bn_relu_pool_bwd_apply': [P, P, I, P, P, P, P, P, I, I, I, I, I, I, P, P],
+    'sed_stat_partials': [],
+    'sed_colstats_f32': [P, L, I, P, P],
+    'sed_bn0_aug_mix_fwd': [P, P, P, P, I, P, I, P, I, I, I, P, P],
+    'sed_bn0_bwd_reduce': [P, P, P, P, P, I, P, I, P, I, I, I, P, P],
+    'sed_spec_augment_f32': [P, I, I, I, I, P, I, P, I, P],
+    'sed_reduce_partials': [P, I, L, P, I, F, P],
+    'sed_conv_c1_grid': [],
+    'sed_conv_c1_fwd': [P, P, P, P, I, I, I, I, P],
+    'sed_conv_c1_wgrad': [P, P, P, I, I, I, I, P],
+    'sed_conv_c1_dgrad': [P, P, P, I, I, I, I, P],
+    'sed_linear_partials': [],
+    'sed_linear_small_fwd': [P, P, P, L, I, I, P, P],
+    'sed_linear_small_bwd': [P, P, P, L, I, I, P, P, P, P],
+    'sed_head_pool_fwd': [P, I, I, I, I, I, P, P, P, P, P],
+    'sed_head_pool_bwd': [P, P, P, I, I, I, I, P, P],
+    'sed_head_att_fwd': [P, P, I, I, I, I, I, F, P, P, P, P, P],
+    'sed_head_att_bwd': [P, P, P, P, P, I, I, I, I, F, P, P, P],
+    'sed_bce_fwd_bwd': [P, P, L, F, P, P, P],
+    'sed_adam_amsgrad': [P, P, P, P, P, L, F, F, F, F, I, F, P],
 }
 _RESTYPES = {
     'sed_last_error_string': ctypes.c_char_p,

@@ -255,12 +255,12 @@ logmel_kernel(const InT* __restrict__ wave, int n_clips, int n_samples, int hop,
 template <typename InT, bool kPower>
 int launch_logmel(const InT* wave, int n_clips, int n_samples, int hop, MelBank mel, float* out,
                   cudaStream_t stream, const char* name) {
-  SED_REQUIRE(wave && out, "%s: null pointer", name);
   SED_REQUIRE(n_clips >= 0 && n_samples > kHalf, "%s: need n_samples > %d for reflect padding (got %d)",
               name, kHalf, n_samples);
   SED_REQUIRE(hop > 0 && hop % 2 == 0 && hop <= 2048, "%s: hop must be even and in (0, 2048] (got %d)", name, hop);
   SED_REQUIRE(aligned(out, 4) && aligned(wave, sizeof(InT)), "%s: misaligned pointer", name);
   if (n_clips == 0) return 0;
+  SED_REQUIRE(wave && out, "%s: null pointer", name);
   const int n_frames = n_samples / hop + 1;
   const int chunks = ceil_div(n_frames, kFramesPerChunk);
   const size_t smem = sizeof(float) * (size_t)(2 * kNfft + kSlots * 4 * kBuf + (kFramesPerChunk - 1) * hop + kNfft);

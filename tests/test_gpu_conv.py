@@ -1,11 +1,13 @@
 """-m gpu: tcgen05 implicit-GEMM 3x3 convolution (fwd, dgrad, wgrad, BN statistics) through the
 C ABI against a plain PyTorch fp32 reference evaluated on the same bf16-rounded operands.
-Tolerance: the kernel accumulates in fp32 and rounds once to bf16 (rel 2^-9 = 1.95e-3)."""
+Tolerance: the kernel accumulates in fp32 and rounds once to bf16 (|err| <= 2^-8 * max|y|)."""
 import pytest
 import torch
 import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
+
+BF16_EPS = 2.0 ** -8          # one rounding to bf16: half an ulp is 2^-9 relative to the binade top
 
 SHAPES = [  # (B, H, W, Cin, Cout)
     (2, 101, 64, 64, 64),      # block1.conv2 on a 1 s clip (H tail: 101 = 50*2 + 1)
@@ -33,13 +35,14 @@ def test_conv_fwd_and_stats(B, H, W, Cin, Cout):
     y, stats = conv.conv3x3(x, wf, Cout, want_stats=True)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), padding=1).permute(0, 2, 3, 1)
     err = (y.float() - ref).abs().max().item()
-    assert err <= 2e-3 * ref.abs().max().item() + 1e-3, err
+    assert err <= BF16_EPS * ref.abs().max().item() + 1e-3, err
     s = stats.double().sum(dim=0)                 # (2, Cout)
     n = B * H * W
     mean_ref = ref.double().mean(dim=(0, 1, 2))
     sq_ref = (ref.double() ** 2).mean(dim=(0, 1, 2))
-    assert torch.allclose(s[0] / n, mean_ref, atol=1e-4, rtol=1e-4)
-    assert torch.allclose(s[1] / n, sq_ref, atol=1e-4, rtol=1e-4)
+    e0 = (s[0] / n - mean_ref).abs().max().item()
+    e1 = ((s[1] / n - sq_ref).abs() / sq_ref).max().item()
+    assert e0 <= 2e-4 and e1 <= 2e-4, (e0, e1)
 
 
 @pytest.mark.parametrize('B,H,W,Cin,Cout', SHAPES)
@@ -51,7 +54,7 @@ def test_conv_dgrad(B, H, W, Cin, Cout):
     dx = conv.conv3x3(dy, wd, Cin)
     ref = F.conv_transpose2d(dy.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), padding=1).permute(0, 2, 3, 1)
     err = (dx.float() - ref).abs().max().item()
-    assert err <= 2e-3 * ref.abs().max().item() + 1e-3, err
+    assert err <= BF16_EPS * ref.abs().max().item() + 1e-3, err
 
 
 @pytest.mark.parametrize('B,H,W,Cin,Cout', SHAPES)

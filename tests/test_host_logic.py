@@ -1,0 +1,121 @@
+"""CPU-only tests of the product's host logic (no kernels run): frozen-parameter construction,
+SpecAugment RNG replay, C-ABI export surface."""
+import ctypes
+import os
+import re
+import time
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_frozen_parameters_equal_oracle():
+    from oracle import frontend as ofe
+    from sound_event_detection_dcase2017_task4_b200 import frontend as pfe
+    assert np.array_equal(ofe.slaney_mel_filterbank(32000, 1024, 64, 50, 14000).T,
+                          pfe.mel_weight_matrix(32000, 1024, 64, 50, 14000))
+    wr, wi = ofe.hann_dft_conv_weights(1024, 1024)
+    pr, pi = pfe.dft_conv_weights(1024, 1024)
+    assert np.array_equal(wr, pr) and np.array_equal(wi, pi)
+
+
+def test_mel_csr_is_exact():
+    from sound_event_detection_dcase2017_task4_b200 import frontend as pfe
+    w = pfe.mel_weight_matrix(32000, 1024, 64, 50, 14000)
+    bank = pfe.MelBankCSR(torch.from_numpy(w))
+    assert bank.w.numel() == 866 and bank.n_bins == 513 and bank.n_mels == 64
+    dense = np.zeros_like(w)
+    lo, off, taps = bank.lo.numpy(), bank.off.numpy(), bank.w.numpy()
+    for m in range(64):
+        dense[lo[m]:lo[m] + off[m + 1] - off[m], m] = taps[off[m]:off[m + 1]]
+    assert np.array_equal(dense, w)
+
+
+def test_int16_fp32_division_matches_reference_conversion():
+    """The kernel converts PCM with a correctly-rounded fp32 division; utils/utilities.py:66-67
+    divides in float64 and casts.  They agree on every int16 value."""
+    pcm = np.arange(-32768, 32768, dtype=np.int32).astype(np.int16)
+    ref = (pcm / 32767.).astype(np.float32)
+    dev = pcm.astype(np.float32) / np.float32(32767.0)
+    assert np.array_equal(ref, dev)
+
+
+def test_specaug_replay_is_bit_exact_and_advances_generator():
+    from oracle import frontend as ofe
+    from sound_event_detection_dcase2017_task4_b200 import specaug
+    for seed in (1, 7, 2024):
+        torch.manual_seed(seed)
+        t_ref = ofe.draw_stripes(37, 1001, 64, 2).numpy()
+        f_ref = ofe.draw_stripes(37, 64, 8, 2).numpy()
+        tail_ref = torch.randint(0, 1 << 30, (4,))
+        torch.manual_seed(seed)
+        t, f = specaug.draw_spec_augment(37, 1001, 64)
+        tail = torch.randint(0, 1 << 30, (4,))
+        assert np.array_equal(t, t_ref) and np.array_equal(f, f_ref)      # index-valued: bit exact
+        assert torch.equal(tail, tail_ref)                                # global RNG stream preserved
+    assert specaug._fast_ok is True
+
+
+def test_specaug_replay_crosses_mt19937_refill():
+    from oracle import frontend as ofe
+    from sound_event_detection_dcase2017_task4_b200 import specaug
+    torch.manual_seed(3)
+    ref = ofe.draw_stripes(400, 1001, 64, 2).numpy()          # 1600 draws > 624-word state
+    torch.manual_seed(3)
+    got = specaug.draw_stripes(400, 1001, 64, 2)
+    assert np.array_equal(got, ref)
+
+
+def test_specaug_replay_is_fast():
+    from sound_event_detection_dcase2017_task4_b200 import specaug
+    specaug.draw_spec_augment(4, 1001, 64)
+    t0 = time.perf_counter()
+    specaug.draw_spec_augment(512, 1001, 64)
+    assert time.perf_counter() - t0 < 0.05
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, 'include', 'sed_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(sed_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from sound_event_detection_dcase2017_task4_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        from sound_event_detection_dcase2017_task4_b200 import build
+        build.build()
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(handle, name), 'declared in include/sed_b200.h but not exported: %s' % name
+    assert sorted(_lib.SIGNATURES) == declared, set(_lib.SIGNATURES) ^ set(declared)
+    assert handle.sed_abi_version() == 1
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, 'sound_event_detection_dcase2017_task4_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith('.py'):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), f
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from sound_event_detection_dcase2017_task4_b200 import _lib
+    monkeypatch.setattr(_lib, '_lib', None)
+    monkeypatch.setattr(_lib, 'LIB_PATH', '/nonexistent/libsedb200.so')
+    with pytest.raises(RuntimeError, match='no CPU'):
+        _lib.lib()
+
+
+def test_cpu_tensor_is_rejected():
+    from sound_event_detection_dcase2017_task4_b200 import frontend as pfe
+    bank = pfe.MelBankCSR(torch.from_numpy(pfe.mel_weight_matrix(32000, 1024, 64, 50, 14000)))
+    with pytest.raises(RuntimeError, match='CUDA'):
+        pfe.logmel(torch.zeros(1, 6400), 320, bank)
