@@ -144,7 +144,7 @@ int sed_linear_partials(void);
 int sed_linear_small_fwd(const float* x, const float* W, const float* bias, long long R, int C, int K, float* out,
                          sed_stream_t stream);
 int sed_linear_small_bwd(const float* dout, const float* x, const float* W, long long R, int C, int K, float* dx,
-                         float* partial_w, float* partial_b, sed_stream_t stream);
+                         int dx_accumulate, float* partial_w, float* partial_b, sed_stream_t stream);
 int sed_head_pool_fwd(const float* logit, int B, int T, int K, int ratio, int mode, float* prob, float* clip,
                       int* argmax, float* frame, sed_stream_t stream);
 int sed_head_pool_bwd(const float* prob, const float* dclip, const int* argmax, int B, int T, int K, int mode,
@@ -161,6 +161,30 @@ int sed_bce_fwd_bwd(const float* prob, const float* target, long long n, float g
 int sed_adam_amsgrad(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq,
                      long long n, float lr, float beta1, float beta2, float eps, int step, float grad_scale,
                      sed_stream_t stream);
+
+
+/* ---- plain tensor-core GEMMs on the conv pipelines (GRU / attention projections) ---------------
+ * sed_gemm_tc:    out[M][N] (fp32) = A[M][K] * Bw[N][K]^T (+ bias[N]);  A, Bw bf16 K-major.
+ * sed_gemm_tn_tc: slabs[s][M][N] (fp32 split-K partials) = A[R][lda>=M]^T * Bm[R][ldb>=N]; bf16.
+ * sed_split_bf16x3: fp32 (R,K) -> bf16 (R,3K) = [hi|lo|hi] (which=0) or [hi|hi|lo] (which=1) so
+ *   that A'.B'^T = hi.hi + lo.hi + hi.lo, an fp32-accurate product on the bf16 tensor cores. */
+int sed_gemm_tc(const void* a, const void* bw, const float* bias, float* out, long long M, int N, int K,
+                sed_stream_t stream);
+int sed_gemm_tn_tc_splits(long long R, int M, int N);
+int sed_gemm_tn_tc(const void* a, int lda, const void* bm, int ldb, float* slabs, long long R, int M, int N,
+                   sed_stream_t stream);
+int sed_split_bf16x3(const float* x, long long R, int K, int which, void* out, sed_stream_t stream);
+int sed_transpose_to_bf16(const float* x, int R, int C, void* out, sed_stream_t stream);
+int sed_colsum_f32(const float* x, long long rows, int C, float* partial, sed_stream_t stream);
+
+/* ---- bidirectional GRU recurrence: nn.GRU(512, 256, bidirectional) (pytorch/models.py:437-438,
+ * :529-530; calls :475, :566).  gx = x W_ih^T + b_ih for both directions (B,T,2,3H), gate order
+ * r,z,n; w_hh (2,3H,H), b_hh (2,3H); out (B,T,2H); gates (B,T,2,4,H) saved for the backward.
+ * bwd: carry = (2,2,B,H) scratch; writes dgx, dgh (B,T,2,3H) and hprev (B,T,2,H). */
+int sed_gru_fwd(const float* gx, const float* w_hh, const float* b_hh, float* out, float* gates, int B, int T,
+                int H, sed_stream_t stream);
+int sed_gru_bwd(const float* dout, const float* out, const float* gates, const float* w_hh, float* carry,
+                float* dgx, float* dgh, float* hprev, int B, int T, int H, sed_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -50,12 +50,20 @@ SIGNATURES = {
     'sed_conv_c1_dgrad': [P, P, P, I, I, I, I, P],
     'sed_linear_partials': [],
     'sed_linear_small_fwd': [P, P, P, L, I, I, P, P],
-    'sed_linear_small_bwd': [P, P, P, L, I, I, P, P, P, P],
+    'sed_linear_small_bwd': [P, P, P, L, I, I, P, I, P, P, P],
     'sed_head_pool_fwd': [P, I, I, I, I, I, P, P, P, P, P],
     'sed_head_pool_bwd': [P, P, P, I, I, I, I, P, P],
     'sed_head_att_fwd': [P, P, I, I, I, I, I, F, P, P, P, P, P],
     'sed_head_att_bwd': [P, P, P, P, P, I, I, I, I, F, P, P, P],
     'sed_bce_fwd_bwd': [P, P, L, F, P, P, P],
+    'sed_gemm_tc': [P, P, P, P, L, I, I, P],
+    'sed_gemm_tn_tc_splits': [L, I, I],
+    'sed_gemm_tn_tc': [P, I, P, I, P, L, I, I, P],
+    'sed_split_bf16x3': [P, L, I, I, P, P],
+    'sed_transpose_to_bf16': [P, I, I, P, P],
+    'sed_colsum_f32': [P, L, I, P, P],
+    'sed_gru_fwd': [P, P, P, P, P, I, I, I, P],
+    'sed_gru_bwd': [P, P, P, P, P, P, P, P, I, I, I, P],
     'sed_adam_amsgrad': [P, P, P, P, P, L, F, F, F, F, I, F, P],
 }
 _RESTYPES = {

@@ -51,9 +51,13 @@ struct ConvParams {
   int kb_per_tap;    // Cin / 64
   __nv_bfloat16* y;  // NHWC output
   float* stats;      // [gridDim.x][2][Cout] partial (sum, sumsq) or nullptr
+  // plain-GEMM mode (kGemm): D[M][N] = A[M][K] * B[N][K]^T (+ bias[N]), fp32 row-major output
+  int gemm_m, gemm_kb;        // rows of A, K / 64
+  float* out_f32;
+  const float* bias;
 };
 
-template <int kN>
+template <int kN, bool kGemm>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const ConvParams p) {
@@ -67,7 +71,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_kb = 9 * p.kb_per_tap;
+  const int num_kb = kGemm ? p.gemm_kb : 9 * p.kb_per_tap;
 
   for (int i = threadIdx.x; i < 2 * p.Cout; i += kNumThreads) s_stats[i] = 0.f;
   if (warp == 0 && elect_one()) {
@@ -99,6 +103,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int m_tile = tile / p.tiles_n;
         const int b = m_tile / p.tiles_h;
         const int h0 = (m_tile % p.tiles_h) * p.bh;
+        if (kGemm) {
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * C::kStageBytes;
+            uint8_t* sb = sa + kABytes;
+            mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
+            tma_load_4d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m_tile * kBlockM, 0, 0);
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kBlockK, n_tile * kN);
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          }
+          continue;
+        }
         for (int tap = 0; tap < 9; ++tap) {
           const int kh = tap / 3, kw = tap % 3;
           for (int cb = 0; cb < p.kb_per_tap; ++cb) {
@@ -159,6 +175,28 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const bool valid = h < p.H;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
+      if (kGemm) {
+        const long long m = (long long)m_tile * kBlockM + row;
+        const bool ok = m < p.gemm_m;
+        float* drow = p.out_f32 + m * p.Cout + n_tile * kN;
+#pragma unroll 1
+        for (int c = 0; c < kN / 32; ++c) {
+          float v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kN + c * 32, v);
+          if (ok) {
+            if (p.bias) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + n_tile * kN + c * 32 + i);
+            }
+            float4* d4 = reinterpret_cast<float4*>(drow + c * 32);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) d4[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+          }
+        }
+        tcgen05_fence_before();
+        mbar_arrive(&tmem_empty_bar[acc]);
+        continue;
+      }
       __nv_bfloat16* dst = p.y + (((long long)b * p.H + h) * p.W + r_w) * p.Cout + n_tile * kN;
 #pragma unroll 1
       for (int c = 0; c < kN / 32; ++c) {
@@ -219,9 +257,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   }
 }
 
-template <int kN>
+template <int kN, bool kGemm = false>
 int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, int grid, cudaStream_t stream) {
-  auto kern = conv3x3_tc_kernel<kN>;
+  auto kern = conv3x3_tc_kernel<kN, kGemm>;
   SED_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<kN>::kDynSmem));
   kern<<<grid, kNumThreads, Cfg<kN>::kDynSmem, stream>>>(ta, tb, p);
   SED_LAUNCH_CHECK("conv3x3_tc_kernel");
@@ -263,6 +301,7 @@ int sed_conv3x3_tc_fwd(const void* x, const void* wpack, void* y, float* stats_p
   p.kb_per_tap = Cin / 64;
   p.y = reinterpret_cast<__nv_bfloat16*>(y);
   p.stats = stats_partial;
+  p.gemm_m = 0; p.gemm_kb = 0; p.out_f32 = nullptr; p.bias = nullptr;
   const int grid = sed_conv3x3_tc_grid(B, H, W, Cout);
 
   alignas(64) CUtensorMap ta, tb;
@@ -285,6 +324,50 @@ int sed_conv3x3_tc_fwd(const void* x, const void* wpack, void* y, float* stats_p
     case 256: return launch_conv<256>(ta, tb, p, grid, s);
   }
   SED_REQUIRE(false, "sed_conv3x3_tc_fwd: no kernel for N tile %d", kN);
+}
+
+
+// Plain tensor-core GEMM on the same pipeline: out[M][N] = A[M][K] * Bw[N][K]^T (+ bias), A / Bw bf16
+// K-major, out fp32.  K % 64 == 0, N in {64, 128} or a multiple of 256.  Used for the GRU / attention
+// projections (x @ W^T), optionally with the 3-way bf16 split (see sed_split_bf16x3) for fp32-class accuracy.
+int sed_gemm_tc(const void* a, const void* bw, const float* bias, float* out, long long M, int N, int K,
+                sed_stream_t stream) {
+  SED_REQUIRE(a && bw && out, "sed_gemm_tc: null pointer");
+  SED_REQUIRE(M > 0 && M < (1LL << 31), "sed_gemm_tc: bad M");
+  SED_REQUIRE(K % 64 == 0 && K >= 64, "sed_gemm_tc: K=%d must be a multiple of 64", K);
+  SED_REQUIRE(N == 64 || N == 128 || N % 256 == 0, "sed_gemm_tc: N=%d unsupported", N);
+  SED_REQUIRE(aligned(out, 16), "sed_gemm_tc: output must be 16-byte aligned");
+  const int kN = N >= 256 ? 256 : N;
+  ConvParams p;
+  p.B = 1; p.H = 1; p.W = 128; p.Cin = K; p.Cout = N;
+  p.bh = 1;
+  p.tiles_h = (int)((M + 127) / 128);
+  p.tiles_n = N / kN;
+  p.num_tiles = p.tiles_h * p.tiles_n;
+  p.kb_per_tap = 0;
+  p.y = nullptr; p.stats = nullptr;
+  p.gemm_m = (int)M; p.gemm_kb = K / 64; p.out_f32 = out; p.bias = bias;
+  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  alignas(64) CUtensorMap ta, tb;
+  {
+    const uint64_t dims[4] = {(uint64_t)K, (uint64_t)M, 1, 1};
+    const uint64_t strides[3] = {(uint64_t)K * 2, (uint64_t)M * K * 2, (uint64_t)M * K * 2};
+    const uint32_t box[4] = {64, 128, 1, 1};
+    if (int rc = tc::make_tmap_bf16(&ta, a, 4, dims, strides, box, "gemm A map")) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    const uint64_t strides[1] = {(uint64_t)K * 2};
+    const uint32_t box[2] = {64, (uint32_t)kN};
+    if (int rc = tc::make_tmap_bf16(&tb, bw, 2, dims, strides, box, "gemm B map")) return rc;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (kN) {
+    case 64: return launch_conv<64, true>(ta, tb, p, grid, s);
+    case 128: return launch_conv<128, true>(ta, tb, p, grid, s);
+    case 256: return launch_conv<256, true>(ta, tb, p, grid, s);
+  }
+  SED_REQUIRE(false, "sed_gemm_tc: no kernel for N tile %d", kN);
 }
 
 }  // extern "C"

@@ -39,6 +39,7 @@ struct WgradParams {
   int bh, tiles_h;
   int m_tiles, n_tiles, splits;
   int a_slabs;             // 2, or 1 when Cout == 64 (upper 64 accumulator rows are ignored)
+  int gemm;                // 1: plain out[M][N] = A[R][M]^T * B[R][N] (one "tap", rows tiled by 128)
   int k_total;             // B * tiles_h pixel tiles
   float* out;              // [splits][9][Cout][Cin]
   long long slab_stride;   // 9*Cout*Cin
@@ -95,11 +96,19 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __gri
         uint8_t* sa = smem + stage * C::kStageBytes;
         uint8_t* sb = sa + 2 * kSlabBytes;
         mbar_arrive_expect_tx(&full_bar[stage], bytes);
-        for (int s = 0; s < p.a_slabs; ++s)
-          tma_load_4d(sa + s * kSlabBytes, &tmap_dy, &full_bar[stage], m_tile * 128 + s * 64, 0, h0, b);
+        if (p.gemm) {
+          for (int s = 0; s < p.a_slabs; ++s)
+            tma_load_4d(sa + s * kSlabBytes, &tmap_dy, &full_bar[stage], m_tile * 128 + s * 64, kt * 128, 0, 0);
 #pragma unroll
-        for (int s = 0; s < C::kBSlabs; ++s)
-          tma_load_4d(sb + s * kSlabBytes, &tmap_x, &full_bar[stage], n_tile * kN + s * 64, kw - 1, h0 + kh - 1, b);
+          for (int s = 0; s < C::kBSlabs; ++s)
+            tma_load_4d(sb + s * kSlabBytes, &tmap_x, &full_bar[stage], n_tile * kN + s * 64, kt * 128, 0, 0);
+        } else {
+          for (int s = 0; s < p.a_slabs; ++s)
+            tma_load_4d(sa + s * kSlabBytes, &tmap_dy, &full_bar[stage], m_tile * 128 + s * 64, 0, h0, b);
+#pragma unroll
+          for (int s = 0; s < C::kBSlabs; ++s)
+            tma_load_4d(sb + s * kSlabBytes, &tmap_x, &full_bar[stage], n_tile * kN + s * 64, kw - 1, h0 + kh - 1, b);
+        }
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
     }
@@ -202,6 +211,7 @@ int sed_conv3x3_tc_wgrad(const void* dy, const void* x, float* slabs, int B, int
   p.n_tiles = Cin / kN;
   p.splits = sed_conv3x3_tc_wgrad_splits(B, H, W, Cin, Cout);
   p.a_slabs = Cout == 64 ? 1 : 2;
+  p.gemm = 0;
   p.k_total = B * p.tiles_h;
   p.out = slabs;
   p.slab_stride = 9LL * Cout * Cin;
@@ -223,6 +233,58 @@ int sed_conv3x3_tc_wgrad(const void* dy, const void* x, float* slabs, int B, int
   cudaStream_t s = (cudaStream_t)stream;
   if (kN == 128) return launch_wgrad<128>(tdy, tx, p, grid, s);
   return launch_wgrad<64>(tdy, tx, p, grid, s);
+}
+
+
+// out[M][N] = A[R][M]^T * Bm[R][N]  (A, Bm bf16 row-major, i.e. both "MN-major" with the reduction
+// index R strided): the weight-gradient GEMMs of the GRU / attention projections
+// (dW = dOut^T X).  Split-K slabs [splits][M][N] fp32; reduce with sed_reduce_partials.
+int sed_gemm_tn_tc_splits(long long R, int M, int N) {
+  const int kN = N >= 128 ? 128 : 64;
+  const int items = ((M + 127) / 128) * (N / kN);
+  const long long k_total = (R + 127) / 128;
+  long long splits = (2LL * sm_count() + items - 1) / items;
+  if (splits > k_total) splits = k_total;
+  if (splits < 1) splits = 1;
+  return (int)splits;
+}
+
+int sed_gemm_tn_tc(const void* a, int lda, const void* bm, int ldb, float* slabs, long long R, int M, int N,
+                   sed_stream_t stream) {
+  SED_REQUIRE(a && bm && slabs, "sed_gemm_tn_tc: null pointer");
+  SED_REQUIRE(R > 0 && R < (1LL << 31), "sed_gemm_tn_tc: bad R");
+  SED_REQUIRE(M == 64 || M % 128 == 0, "sed_gemm_tn_tc: M=%d unsupported", M);
+  SED_REQUIRE(N == 64 || N % 128 == 0, "sed_gemm_tn_tc: N=%d unsupported", N);
+  SED_REQUIRE(lda >= M && ldb >= N && lda % 8 == 0 && ldb % 8 == 0, "sed_gemm_tn_tc: bad leading dimensions");
+  const int kN = N >= 128 ? 128 : 64;
+  WgradParams p;
+  p.B = 1; p.H = 1; p.W = 128; p.Cin = N; p.Cout = M;
+  p.bh = 1; p.tiles_h = (int)((R + 127) / 128);
+  p.m_tiles = (M + 127) / 128;
+  p.n_tiles = N / kN;
+  p.splits = sed_gemm_tn_tc_splits(R, M, N);
+  p.a_slabs = M == 64 ? 1 : 2;
+  p.gemm = 1;
+  p.k_total = p.tiles_h;
+  p.out = slabs;
+  p.slab_stride = (long long)M * N;
+  const int grid = p.m_tiles * p.n_tiles * p.splits;       // tap index is always 0
+  alignas(64) CUtensorMap ta, tb;
+  {
+    const uint64_t dims[4] = {(uint64_t)M, (uint64_t)R, 1, 1};
+    const uint64_t strides[3] = {(uint64_t)lda * 2, (uint64_t)R * lda * 2, (uint64_t)R * lda * 2};
+    const uint32_t box[4] = {64, 128, 1, 1};
+    if (int rc = tc::make_tmap_bf16(&ta, a, 4, dims, strides, box, "gemm_tn A map")) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)N, (uint64_t)R, 1, 1};
+    const uint64_t strides[3] = {(uint64_t)ldb * 2, (uint64_t)R * ldb * 2, (uint64_t)R * ldb * 2};
+    const uint32_t box[4] = {64, 128, 1, 1};
+    if (int rc = tc::make_tmap_bf16(&tb, bm, 4, dims, strides, box, "gemm_tn B map")) return rc;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (kN == 128) return launch_wgrad<128>(ta, tb, p, grid, s);
+  return launch_wgrad<64>(ta, tb, p, grid, s);
 }
 
 }  // extern "C"

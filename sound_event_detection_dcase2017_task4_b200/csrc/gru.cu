@@ -1,0 +1,262 @@
+// gru.cu -- bidirectional single-layer GRU recurrence (forward + BPTT) and the small layout /
+// precision helpers around its tensor-core projections.
+//
+// Replaces cuDNN's RNN behind `nn.GRU(512, 256, num_layers=1, bias=True, batch_first=True,
+// bidirectional=True)` (/root/reference/pytorch/models.py:437-438 / :529-530, call :475 / :566):
+//   r = sigmoid(W_ir x + b_ir + W_hr h + b_hr)        z = sigmoid(W_iz x + b_iz + W_hz h + b_hz)
+//   n = tanh(W_in x + b_in + r * (W_hn h + b_hn))     h' = (1 - z) * n + z * h        (gate order r, z, n)
+//
+// Split of the work:
+//   * input projections for all time steps and both directions: ONE tensor-core GEMM
+//     (B*T, 512) x (512, 1536) with the 3-way bf16 operand split (sed_split_bf16x3 + sed_gemm_tc);
+//   * the recurrence: per time step ONE launch covering both directions; CTA = (direction,
+//     16 batch rows, 32 hidden units); its 96 x 256 slice of W_hh and the 16 previous hidden rows sit
+//     in shared memory; gate math in fp32.  Saves (r, z, n, W_hn h + b_hn) for the backward.
+//   * BPTT: per step ONE launch; CTA = (direction, 16 batch rows, 32 columns of W_hh); the gate
+//     gradients of the 16 rows are rebuilt in shared memory, then dh_prev = dgh . W_hh (+ dh * z).
+//   * weight gradients after the loop: tensor-core TN GEMMs (sed_gemm_tn_tc) over all (b, t).
+#include "common.cuh"
+
+namespace sed {
+namespace {
+
+constexpr int kBT = 16;       // batch rows per CTA
+constexpr int kHT = 32;       // hidden units (fwd) / W_hh columns (bwd) per CTA
+constexpr int kGruThreads = kBT * kHT;
+
+__device__ __forceinline__ float sigm(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+// Gx (B,T,2,3H) | Whh (2,3H,H) | bhh (2,3H) | out (B,T,2H) | gates (B,T,2,4,H) = r,z,n,ghn
+__global__ void __launch_bounds__(kGruThreads)
+gru_fwd_step_kernel(const float* __restrict__ Gx, const float* __restrict__ Whh, const float* __restrict__ bhh,
+                    float* __restrict__ out, float* __restrict__ gates, int B, int T, int H, int s) {
+  extern __shared__ __align__(16) float smem[];
+  const int ldw = H + 4;
+  float* sW = smem;                      // [3*kHT][H+4]
+  float* sH = smem + 3 * kHT * ldw;      // [kBT][H]
+  const int d = blockIdx.z, b0 = blockIdx.y * kBT, j0 = blockIdx.x * kHT;
+  const int tt = d == 0 ? s : T - 1 - s;
+  const int tp = d == 0 ? tt - 1 : tt + 1;
+  const int tid = threadIdx.x;
+  const float* W = Whh + (long long)d * 3 * H * H;
+  for (int i = tid; i < 3 * kHT * (H / 4); i += kGruThreads) {
+    const int row = i / (H / 4), k4 = i % (H / 4);
+    const int g = row / kHT, jl = row % kHT;
+    const float4 v = *reinterpret_cast<const float4*>(W + ((long long)(g * H + j0 + jl)) * H + k4 * 4);
+    *reinterpret_cast<float4*>(sW + row * ldw + k4 * 4) = v;
+  }
+  for (int i = tid; i < kBT * (H / 4); i += kGruThreads) {
+    const int bl = i / (H / 4), k4 = i % (H / 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (s > 0 && b0 + bl < B)
+      v = *reinterpret_cast<const float4*>(out + ((long long)(b0 + bl) * T + tp) * 2 * H + d * H + k4 * 4);
+    *reinterpret_cast<float4*>(sH + bl * H + k4 * 4) = v;
+  }
+  __syncthreads();
+  const int bl = tid / kHT, jl = tid % kHT;
+  const int b = b0 + bl, j = j0 + jl;
+  if (b >= B) return;
+  float ar = 0.f, az = 0.f, an = 0.f;
+  const float* hrow = sH + bl * H;
+  const float* wr = sW + (0 * kHT + jl) * ldw;
+  const float* wz = sW + (1 * kHT + jl) * ldw;
+  const float* wn = sW + (2 * kHT + jl) * ldw;
+  for (int k = 0; k < H; k += 4) {
+    const float4 h4 = *reinterpret_cast<const float4*>(hrow + k);
+    const float4 r4 = *reinterpret_cast<const float4*>(wr + k);
+    const float4 z4 = *reinterpret_cast<const float4*>(wz + k);
+    const float4 n4 = *reinterpret_cast<const float4*>(wn + k);
+    ar = fmaf(h4.x, r4.x, ar); ar = fmaf(h4.y, r4.y, ar); ar = fmaf(h4.z, r4.z, ar); ar = fmaf(h4.w, r4.w, ar);
+    az = fmaf(h4.x, z4.x, az); az = fmaf(h4.y, z4.y, az); az = fmaf(h4.z, z4.z, az); az = fmaf(h4.w, z4.w, az);
+    an = fmaf(h4.x, n4.x, an); an = fmaf(h4.y, n4.y, an); an = fmaf(h4.z, n4.z, an); an = fmaf(h4.w, n4.w, an);
+  }
+  const float* bh = bhh + d * 3 * H;
+  const float* gx = Gx + (((long long)b * T + tt) * 2 + d) * 3 * H;
+  const float ghn = an + bh[2 * H + j];
+  const float r = sigm(gx[j] + ar + bh[j]);
+  const float z = sigm(gx[H + j] + az + bh[H + j]);
+  const float n = tanhf(gx[2 * H + j] + r * ghn);
+  const float hp = hrow[j];
+  out[((long long)b * T + tt) * 2 * H + d * H + j] = (1.f - z) * n + z * hp;
+  float* gs = gates + (((long long)b * T + tt) * 2 + d) * 4 * H;
+  gs[j] = r; gs[H + j] = z; gs[2 * H + j] = n; gs[3 * H + j] = ghn;
+}
+
+// dout (B,T,2H) | carry_in/out (2,B,H) | dGx, dGh (B,T,2,3H) | Hprev (B,T,2,H)
+__global__ void __launch_bounds__(kGruThreads)
+gru_bwd_step_kernel(const float* __restrict__ dout, const float* __restrict__ out, const float* __restrict__ gates,
+                    const float* __restrict__ Whh, const float* __restrict__ carry_in, float* __restrict__ carry_out,
+                    float* __restrict__ dGx, float* __restrict__ dGh, float* __restrict__ Hprev, int B, int T, int H,
+                    int bs) {
+  extern __shared__ __align__(16) float smem[];
+  float* sW = smem;                      // [3H][kHT]
+  float* sD = smem + 3 * H * kHT;        // [kBT][3H]   dgh
+  float* sC = sD + kBT * 3 * H;          // [kBT][kHT]  dh*z for this CTA's columns
+  const int d = blockIdx.z, b0 = blockIdx.y * kBT, k0 = blockIdx.x * kHT;
+  const int tt = d == 0 ? T - 1 - bs : bs;
+  const int tp = d == 0 ? tt - 1 : tt + 1;             // time index of h_prev (may be out of range)
+  const bool has_prev = tp >= 0 && tp < T;
+  const int tid = threadIdx.x;
+  const float* W = Whh + (long long)d * 3 * H * H;
+  for (int i = tid; i < 3 * H * (kHT / 4); i += kGruThreads) {
+    const int row = i / (kHT / 4), c4 = i % (kHT / 4);
+    *reinterpret_cast<float4*>(sW + row * kHT + c4 * 4) =
+        *reinterpret_cast<const float4*>(W + (long long)row * H + k0 + c4 * 4);
+  }
+  for (int i = tid; i < kBT * H; i += kGruThreads) {
+    const int bl = i / H, j = i % H;
+    const int b = b0 + bl;
+    float dr_pre = 0.f, dz_pre = 0.f, dn_pre = 0.f, r = 0.f, dhz = 0.f, hp = 0.f;
+    if (b < B) {
+      const long long bt = (long long)b * T + tt;
+      const float* gs = gates + (bt * 2 + d) * 4 * H;
+      r = gs[j];
+      const float z = gs[H + j], n = gs[2 * H + j], ghn = gs[3 * H + j];
+      hp = has_prev ? out[((long long)b * T + tp) * 2 * H + d * H + j] : 0.f;
+      float dh = dout[bt * 2 * H + d * H + j];
+      if (bs > 0) dh += carry_in[((long long)d * B + b) * H + j];
+      dn_pre = dh * (1.f - z) * (1.f - n * n);
+      dz_pre = dh * (hp - n) * z * (1.f - z);
+      dr_pre = dn_pre * ghn * r * (1.f - r);
+      dhz = dh * z;
+      if (blockIdx.x == 0) {
+        float* gx = dGx + (bt * 2 + d) * 3 * H;
+        float* gh = dGh + (bt * 2 + d) * 3 * H;
+        gx[j] = dr_pre; gx[H + j] = dz_pre; gx[2 * H + j] = dn_pre;
+        gh[j] = dr_pre; gh[H + j] = dz_pre; gh[2 * H + j] = dn_pre * r;
+        Hprev[(bt * 2 + d) * H + j] = hp;
+      }
+    }
+    sD[bl * 3 * H + j] = dr_pre;
+    sD[bl * 3 * H + H + j] = dz_pre;
+    sD[bl * 3 * H + 2 * H + j] = dn_pre * r;
+    if (j >= k0 && j < k0 + kHT) sC[bl * kHT + (j - k0)] = dhz;
+  }
+  __syncthreads();
+  const int bl = tid / kHT, kl = tid % kHT;
+  const int b = b0 + bl;
+  if (b >= B) return;
+  float acc = 0.f;
+  const float* drow = sD + bl * 3 * H;
+  for (int row = 0; row < 3 * H; row += 4) {
+    const float4 d4 = *reinterpret_cast<const float4*>(drow + row);
+    acc = fmaf(d4.x, sW[(row + 0) * kHT + kl], acc);
+    acc = fmaf(d4.y, sW[(row + 1) * kHT + kl], acc);
+    acc = fmaf(d4.z, sW[(row + 2) * kHT + kl], acc);
+    acc = fmaf(d4.w, sW[(row + 3) * kHT + kl], acc);
+  }
+  carry_out[((long long)d * B + b) * H + k0 + kl] = acc + sC[bl * kHT + kl];
+}
+
+// (R, K) fp32 -> (R, 3K) bf16:  which = 0: [hi | lo | hi]   (left operand)
+//                               which = 1: [hi | hi | lo]   (right operand)
+// so that  A' . B'^T = hi.hi + lo.hi + hi.lo  ~  fp32-accurate product on the bf16 tensor cores.
+__global__ void split_bf16x3_kernel(const float* __restrict__ x, long long R, int K, int which,
+                                    __nv_bfloat16* __restrict__ out) {
+  const long long n = R * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / K;
+    const int k = (int)(i % K);
+    const float v = x[i];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    __nv_bfloat16* o = out + r * 3 * K;
+    o[k] = hi;
+    o[K + k] = which == 0 ? lo : hi;
+    o[2 * K + k] = which == 0 ? hi : lo;
+  }
+}
+
+// (R, C) fp32 -> (C, R) bf16 (tiled through shared memory)
+__global__ void transpose_to_bf16_kernel(const float* __restrict__ x, int R, int C, __nv_bfloat16* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < C) ? x[(long long)r * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < C) out[(long long)c * R + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+
+// column sums of a (rows, C) fp32 matrix: partial[blk][C]
+__global__ void colsum_kernel(const float* __restrict__ x, long long rows, int C, float* __restrict__ partial) {
+  const long long per = (rows + gridDim.x - 1) / gridDim.x;
+  const long long r0 = blockIdx.x * per, r1 = min(rows, r0 + per);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f;
+    for (long long r = r0; r < r1; ++r) a += x[r * C + c];
+    partial[(long long)blockIdx.x * C + c] = a;
+  }
+}
+
+}  // namespace
+}  // namespace sed
+
+using namespace sed;
+
+extern "C" {
+
+int sed_gru_fwd(const float* gx, const float* w_hh, const float* b_hh, float* out, float* gates, int B, int T,
+                int H, sed_stream_t stream) {
+  SED_REQUIRE(gx && w_hh && b_hh && out && gates, "sed_gru_fwd: null pointer");
+  SED_REQUIRE(H % kHT == 0 && H % 4 == 0 && H <= 512, "sed_gru_fwd: hidden size %d unsupported", H);
+  if (B == 0 || T == 0) return 0;
+  const size_t smem = sizeof(float) * (size_t)(3 * kHT * (H + 4) + kBT * H);
+  SED_CUDA(cudaFuncSetAttribute(gru_fwd_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const dim3 grid(H / kHT, (B + kBT - 1) / kBT, 2);
+  for (int s = 0; s < T; ++s) {
+    gru_fwd_step_kernel<<<grid, kGruThreads, smem, (cudaStream_t)stream>>>(gx, w_hh, b_hh, out, gates, B, T, H, s);
+    SED_LAUNCH_CHECK("gru_fwd_step_kernel");
+  }
+  return 0;
+}
+
+int sed_gru_bwd(const float* dout, const float* out, const float* gates, const float* w_hh, float* carry /* (2,2,B,H) */,
+                float* dgx, float* dgh, float* hprev, int B, int T, int H, sed_stream_t stream) {
+  SED_REQUIRE(dout && out && gates && w_hh && carry && dgx && dgh && hprev, "sed_gru_bwd: null pointer");
+  SED_REQUIRE(H % kHT == 0 && H % 4 == 0 && H <= 256, "sed_gru_bwd: hidden size %d unsupported", H);
+  if (B == 0 || T == 0) return 0;
+  const size_t smem = sizeof(float) * (size_t)(3 * H * kHT + kBT * 3 * H + kBT * kHT);
+  SED_CUDA(cudaFuncSetAttribute(gru_bwd_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const dim3 grid(H / kHT, (B + kBT - 1) / kBT, 2);
+  const long long half = 2LL * B * H;
+  for (int bs = 0; bs < T; ++bs) {
+    const float* cin = carry + (bs & 1) * half;
+    float* cout = carry + ((bs + 1) & 1) * half;
+    gru_bwd_step_kernel<<<grid, kGruThreads, smem, (cudaStream_t)stream>>>(dout, out, gates, w_hh, cin, cout, dgx, dgh,
+                                                                           hprev, B, T, H, bs);
+    SED_LAUNCH_CHECK("gru_bwd_step_kernel");
+  }
+  return 0;
+}
+
+int sed_split_bf16x3(const float* x, long long R, int K, int which, void* out, sed_stream_t stream) {
+  SED_REQUIRE(x && out && (which == 0 || which == 1), "sed_split_bf16x3: bad arguments");
+  if (R * K == 0) return 0;
+  const int grid = (int)min((R * K + 255) / 256, (long long)sm_count() * 8);
+  split_bf16x3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, R, K, which, reinterpret_cast<__nv_bfloat16*>(out));
+  SED_LAUNCH_CHECK("split_bf16x3_kernel");
+  return 0;
+}
+
+int sed_transpose_to_bf16(const float* x, int R, int C, void* out, sed_stream_t stream) {
+  SED_REQUIRE(x && out && R > 0 && C > 0, "sed_transpose_to_bf16: bad arguments");
+  const dim3 grid((C + 31) / 32, (R + 31) / 32);
+  transpose_to_bf16_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, R, C,
+                                                                           reinterpret_cast<__nv_bfloat16*>(out));
+  SED_LAUNCH_CHECK("transpose_to_bf16_kernel");
+  return 0;
+}
+
+int sed_colsum_f32(const float* x, long long rows, int C, float* partial, sed_stream_t stream) {
+  SED_REQUIRE(x && partial && rows >= 1 && C >= 1, "sed_colsum_f32: bad arguments");
+  colsum_kernel<<<sm_count() * 4, 256, 0, (cudaStream_t)stream>>>(x, rows, C, partial);
+  SED_LAUNCH_CHECK("colsum_kernel");
+  return 0;
+}
+
+}  // extern "C"

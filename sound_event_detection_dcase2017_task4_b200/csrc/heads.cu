@@ -43,7 +43,7 @@ __global__ void linear_small_fwd_kernel(const float* __restrict__ x, const float
 
 // dx[r][c] = sum_k dout[r][k] * W[k][c]
 __global__ void linear_small_dx_kernel(const float* __restrict__ dout, const float* __restrict__ W, long long R, int C,
-                                       int K, float* __restrict__ dx) {
+                                       int K, float* __restrict__ dx, int accumulate) {
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -56,7 +56,7 @@ __global__ void linear_small_dx_kernel(const float* __restrict__ dout, const flo
 #pragma unroll
       for (int k = 0; k < kMaxK; ++k)
         if (k < K) a = fmaf(d[k], __ldg(W + (long long)k * C + c), a);
-      dx[r * C + c] = a;
+      dx[r * C + c] = accumulate ? dx[r * C + c] + a : a;
     }
   }
 }
@@ -252,13 +252,13 @@ int sed_linear_small_fwd(const float* x, const float* W, const float* bias, long
 }
 
 int sed_linear_small_bwd(const float* dout, const float* x, const float* W, long long R, int C, int K, float* dx,
-                         float* partial_w, float* partial_b, sed_stream_t stream) {
+                         int dx_accumulate, float* partial_w, float* partial_b, sed_stream_t stream) {
   SED_REQUIRE(dout && x && W, "sed_linear_small_bwd: null pointer");
   SED_REQUIRE(K >= 1 && K <= kMaxK, "sed_linear_small_bwd: K=%d must be in [1, %d]", K, kMaxK);
   if (R == 0) return 0;
   if (dx) {
     const int grid = (int)min((R + 7) / 8, (long long)sm_count() * 8);
-    linear_small_dx_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dout, W, R, C, K, dx);
+    linear_small_dx_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dout, W, R, C, K, dx, dx_accumulate);
     SED_LAUNCH_CHECK("linear_small_dx_kernel");
   }
   if (partial_w) {

@@ -1,0 +1,2 @@
+"""seam B shim: `import pytorch_utils` resolves here when dropin/ is on sys.path (pytorch/main.py:21-27)."""
+from sound_event_detection_dcase2017_task4_b200.pytorch_utils import *  # noqa: F401,F403

@@ -190,16 +190,19 @@ def linear_small_fwd(x2d, W, bias):
     return out
 
 
-def linear_small_bwd(dout, x2d, W, dW, dbias, want_dx=True):
+def linear_small_bwd(dout, x2d, W, dW, dbias, want_dx=True, dx=None):
+    """dx given => accumulate into it (dx += dout @ W)."""
     r, c = x2d.shape
     k = W.shape[0]
-    dx = _empty((r, c), F32, x2d) if want_dx else None
+    acc = 1 if dx is not None else 0
+    if dx is None:
+        dx = _empty((r, c), F32, x2d) if want_dx else None
     with _dev(x2d):
         P = _lib.lib().sed_linear_partials()
         pw = _empty((P, k, c), F32, x2d) if dW is not None else None
         pb = _empty((P, k), F32, x2d) if dbias is not None else None
-        call('sed_linear_small_bwd', dout.data_ptr(), x2d.data_ptr(), W.data_ptr(), r, c, k, ptr(dx), ptr(pw),
-             ptr(pb), stream_of(x2d))
+        call('sed_linear_small_bwd', dout.data_ptr(), x2d.data_ptr(), W.data_ptr(), r, c, k, ptr(dx), acc,
+             ptr(pw), ptr(pb), stream_of(x2d))
     if dW is not None:
         reduce_partials(pw, dW)
     if dbias is not None:

@@ -1,0 +1,73 @@
+"""-m gpu: GRU recurrence, tensor-core projections and the fused Adam against PyTorch fp32."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_gemm_nt_split3_is_fp32_accurate():
+    from sound_event_detection_dcase2017_task4_b200 import gemm
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1000, 512, generator=g).cuda()
+    w = torch.randn(768, 512, generator=g).cuda() * 0.05
+    b = torch.randn(768, generator=g).cuda()
+    ref = (x.double() @ w.double().t() + b.double()).float()
+    got = gemm.linear_x3(x, w, b)
+    assert (got - ref).abs().max().item() <= 2e-5 * ref.abs().max().item() + 1e-5
+    one = gemm.gemm_nt(x.to(torch.bfloat16), w.to(torch.bfloat16))
+    ref1 = x.to(torch.bfloat16).float() @ w.to(torch.bfloat16).float().t()
+    assert (one - ref1).abs().max().item() <= 1e-3
+
+
+def test_gemm_tn():
+    from sound_event_detection_dcase2017_task4_b200 import gemm
+    g = torch.Generator().manual_seed(1)
+    a = torch.randn(1000, 1536, generator=g).cuda().to(torch.bfloat16)
+    b = torch.randn(1000, 512, generator=g).cuda().to(torch.bfloat16)
+    out = torch.empty(768, 256, device='cuda')
+    gemm.gemm_tn(a, b, 768, 256, out, a_col=768, b_col=256)
+    ref = a[:, 768:].float().t() @ b[:, 256:].float()
+    assert (out - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize('B,T', [(3, 12), (20, 125)])
+def test_gru_fwd_bwd_vs_torch(B, T):
+    from sound_event_detection_dcase2017_task4_b200 import temporal
+    torch.manual_seed(0)
+    gru = torch.nn.GRU(512, 256, num_layers=1, bias=True, batch_first=True, bidirectional=True).cuda()
+    for n, p in gru.named_parameters():
+        if 'bias' in n:
+            torch.nn.init.uniform_(p, -0.1, 0.1)
+    x = torch.randn(B, T, 512, device='cuda') * 0.5
+    xr = x.clone().requires_grad_(True)
+    ref, _ = gru(xr)
+    dout = torch.randn_like(ref)
+    ref.backward(dout)
+    out, ctx = temporal.gru_forward(gru, x, keep=True)
+    assert (out - ref).abs().max().item() <= 1e-4
+    grads = {}
+    ref_grads = {n: p.grad.clone() for n, p in gru.named_parameters()}
+
+    def grad_of(p):
+        return grads.setdefault(p, torch.empty_like(p))
+
+    dx = temporal.gru_backward(gru, ctx, dout, grad_of)
+    assert (dx - xr.grad).norm().item() / xr.grad.norm().item() <= 1e-2
+    for n, p in gru.named_parameters():
+        err = (grads[p] - ref_grads[n]).norm().item() / ref_grads[n].norm().item()
+        assert err <= 1e-2, (n, err)
+
+
+def test_adam_amsgrad_matches_torch():
+    from sound_event_detection_dcase2017_task4_b200 import ops
+    torch.manual_seed(0)
+    p_ref = torch.nn.Parameter(torch.randn(10007, device='cuda'))
+    opt = torch.optim.Adam([p_ref], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0., amsgrad=True)
+    p = p_ref.detach().clone()
+    m, v, vmax = torch.zeros_like(p), torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 6):
+        g = torch.randn_like(p) * (1.0 if step % 2 else 0.01)
+        p_ref.grad = g.clone()
+        opt.step()
+        ops.adam_amsgrad_(p, g, m, v, vmax, 1e-3, 0.9, 0.999, 1e-8, step)
+        assert (p - p_ref.detach()).abs().max().item() <= 2e-6
