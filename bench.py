@@ -1,0 +1,359 @@
+"""bench.py -- the hot path's headline metric on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json metric "10s-clips/sec train Cnn_9layers_Gru_FrameAtt"): one training step
+of Cnn_9layers_Gru_FrameAtt as /root/reference/pytorch/main.py:233-258 runs it with
+``--batch_size 256 --augmentation mixup``: 512 raw 32 kHz x 10 s clips per GPU per step go through
+log-mel / bn0 / SpecAugment, are mixed pairwise to 256 training samples, 4 ConvBlocks, biGRU,
+attention head, clip_bce, backward, one NCCL all-reduce of the flat gradient (N > 1),
+Adam(amsgrad).  ``value`` counts RAW 10 s clips consumed per second over all GPUs (the loader
+feeds 2 x batch_size clips per iteration under mixup, main.py:151-153); training samples/s is
+half of it and is reported as ``train_samples_per_s``.
+
+One JSON line on stdout (rank 0).  ``value``: inputs resident in HBM; ``e2e``: the same step with
+the waveforms/targets/lambda copied from pinned host memory inside the timed region and the loss
+read back to the host every step.  ``roofline``: the 3x3 tensor-core convolution kernel
+(conv3x3_tc_kernel: all forward + data-gradient launches of a step) against the measured bf16
+peak.  ``cpu_baseline`` / ``--impl reference``: the CPU oracle (oracle/sed.py, a restatement of
+the reference's PyTorch modules pinned to the unmodified reference by tests/golden) timed on
+this box's host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+MODEL = 'Cnn_9layers_Gru_FrameAtt'
+CTOR = (32000, 1024, 320, 64, 50, 14000, 17)
+CLIP_SAMPLES = 320000
+METRIC = '10s-clips/sec train %s (raw clips consumed, batch_size 256 + mixup per GPU)' % MODEL
+UNIT = 'clips/s'
+# 3x3 conv FLOPs per training sample of one pass: layers with Cin >= 64
+CONV_TC_LAYERS = [(1001, 64, 64, 64), (500, 32, 64, 128), (500, 32, 128, 128), (250, 16, 128, 256),
+                  (250, 16, 256, 256), (125, 8, 256, 512), (125, 8, 512, 512)]
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {'hbm_gbs': p['hbm_gbs'], 'bf16_burst': p['bf16_tflops'],
+                'bf16_sustained': p.get('bf16_tflops_sustained', p['bf16_tflops']), 'source': 'measured'}
+    return {'hbm_gbs': 6650.0, 'bf16_burst': 1590.0, 'bf16_sustained': 1400.0, 'source': 'fallback'}
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.lines:
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+        return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': max(mx), 'power_w_max': max(power),
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def synthetic_rank_batch(b2, rank):
+    """int16 uniform [-8192, 8191] -> x/32767 fp32, Bernoulli(0.067) targets,
+    RandomState(1234 + rank)."""
+    import numpy as np
+    rs = np.random.RandomState(1234 + rank)
+    pcm = rs.randint(-8192, 8192, size=(b2, CLIP_SAMPLES), dtype=np.int16)
+    target = (rs.rand(b2, 17) < 0.067).astype(np.float32)
+    return pcm, target
+
+
+# ----------------------------------------------------------------------------- reference / CPU arm
+def cpu_oracle_run(steps, warmup, batch_size, threads):
+    """Times the CPU oracle's train step (same model, mixup, Adam-amsgrad) on a bounded sample:
+    ``batch_size`` training samples = 2*batch_size raw clips per step.  Returns clips/s."""
+    import numpy as np
+    import torch
+    from oracle import sed
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    model = sed.build(MODEL)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.,
+                           amsgrad=True)
+    b2 = 2 * batch_size
+    _, wave, target = sed.synthetic_batch(b2, CLIP_SAMPLES, seed=1234)
+    wave, target = torch.from_numpy(wave), torch.from_numpy(target)
+    mix = sed.MixupLambda(1., 1234)
+    times = []
+    for i in range(warmup + steps):
+        lam = torch.Tensor(mix.get_lambda(b2))
+        t0 = time.perf_counter()
+        sed.train_step(model, opt, wave, target, lam)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return b2 * len(times) / total, total / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    bs = 8 if args.steps <= 24 else (4 if args.steps <= 60 else 2)
+    value, sec = cpu_oracle_run(args.steps, args.warmup, bs, threads)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': '%s train step (fwd + clip_bce + bwd + Adam-amsgrad), mixup, 32 kHz x 10 s clips' % MODEL,
+                   'batch_size': bs, 'raw_clips_per_step': 2 * bs},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                         'sample': 'CPU oracle (oracle/sed.py, PyTorch CPU fp32 restatement pinned to the '
+                                   'unmodified reference), %d steps of batch_size %d + mixup = %d raw clips/step'
+                                   % (args.steps, bs, 2 * bs)},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py: no CUDA device; the product path has no CPU fallback '
+                           '(use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    from sound_event_detection_dcase2017_task4_b200 import _lib, models
+    from sound_event_detection_dcase2017_task4_b200.trainer import FusedTrainer
+    from oracle import sed as _unused  # noqa: F401  (cpu_baseline leg only; never on the timed path)
+    _lib.lib()
+
+    bs = args.batch
+    b2 = 2 * bs
+    torch.manual_seed(0)
+    model = getattr(models, MODEL)(*CTOR).to(dev)
+    model.train()
+    trainer = FusedTrainer(model, lr=1e-3, world_size=world)
+
+    pcm, target_np = synthetic_rank_batch(b2, rank)
+    wave_host = torch.from_numpy((pcm / np.float32(32767.)).astype(np.float32)).pin_memory()
+    target_host = torch.from_numpy(target_np).pin_memory()
+    from oracle.sed import MixupLambda
+    lam_gen = MixupLambda(1., 1234 + rank)           # utilities.Mixup's numpy stream (host-side, as in main.py:233)
+    lam_host = torch.empty(b2, dtype=torch.float32).pin_memory()
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    wave_dev = wave_host.to(dev)
+    target_dev = target_host.to(dev)
+    lam_dev = torch.empty(b2, dtype=torch.float32, device=dev)
+
+    def next_lambda():
+        lam_host.copy_(torch.from_numpy(lam_gen.get_lambda(b2).astype(np.float32)))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = _lib.launch_count()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = _lib.launch_count() - n0
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches
+
+    def step_resident():
+        next_lambda()
+        lam_dev.copy_(lam_host, non_blocking=True)      # 2 KB of lambdas: host-generated in the reference too
+        trainer.step(wave_dev, target_dev, lam_dev)
+
+    stage = {}
+
+    def step_e2e():
+        next_lambda()
+        w = wave_host.to(dev, non_blocking=True)
+        t = target_host.to(dev, non_blocking=True)
+        lam_dev.copy_(lam_host, non_blocking=True)
+        loss = trainer.step(w, t, lam_dev)
+        loss_host.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()       # main.py:253 prints the loss every step
+        stage['loss'] = float(loss_host)
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ms, launches = timed(step_resident, args.steps)
+    clock_info = clocks.stop() if rank == 0 else None
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+
+    # ---- roofline leg: per-entry-point device times of one more step (CUDA events on the launch stream)
+    roof = None
+    shares = None
+    if rank == 0:
+        peaks = measured_peaks()
+        agg = {}
+        reps = 3
+        for _ in range(reps):
+            _lib.PROFILE = []
+            step_resident()
+            torch.cuda.synchronize()
+            for name, tag, e0, e1 in _lib.PROFILE:
+                a = agg.setdefault(name, [0, 0.0])
+                a[0] += 1
+                a[1] += e0.elapsed_time(e1)
+            _lib.PROFILE = None
+        total_ms = sum(v[1] for v in agg.values()) / reps
+        shares = {k: {'launches_per_step': v[0] // reps, 'ms_per_step': round(v[1] / reps, 4),
+                      'share': round(v[1] / reps / total_ms, 4)}
+                  for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])}
+        # conv3x3_tc_kernel runs the forward of 7 layers and the data-gradient of 6 (block1.conv2's
+        # dgrad feeds the Cin=1 layer; block1.conv1 itself is a separate direct kernel)
+        fl = [2.0 * h * w * ci * co * 9 for (h, w, ci, co) in CONV_TC_LAYERS]
+        flops_step = bs * (sum(fl) + sum(fl))           # fwd + dgrad of all 7 tensor-core layers
+        n_conv, conv_ms = agg['sed_conv3x3_tc_fwd'][0] / reps, agg['sed_conv3x3_tc_fwd'][1] / reps
+        achieved = flops_step / (conv_ms * 1e-3) / 1e12
+        roof = {'kernel': 'conv3x3_tc_kernel (sed_conv3x3_tc_fwd: forward + data-gradient launches)',
+                'bound': 'tensor', 'achieved': round(achieved, 2), 'peak': peaks['bf16_sustained'],
+                'unit': 'TFLOP/s', 'frac': round(achieved / peaks['bf16_sustained'], 4),
+                'peak_source': peaks['source'] + ' bf16_tflops_sustained (kernel timed inside a long step)',
+                'launches_per_step': n_conv, 'avg_launch_ms': round(conv_ms / n_conv, 4),
+                'flop_per_launch_avg': flops_step / n_conv, 'traffic': None,
+                'share_of_step': round(conv_ms / total_ms, 4)}
+
+    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, sec = cpu_oracle_run(3, 1, 8, threads)
+        cpu = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+               'sample': 'CPU oracle (oracle/sed.py), 1 warm-up + 3 timed steps of batch_size 8 + mixup '
+                         '(16 raw 10 s clips/step), %.2f s/step' % sec}
+
+    if rank == 0:
+        clips = b2 * world * args.steps
+        value = clips / (ms * 1e-3)
+        e2e_value = clips / (ms_e2e * 1e-3)
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'train_samples_per_s': value / 2,
+            'config': {'workload': '%s train step (log-mel, bn0, SpecAugment, mixup, 4 ConvBlocks, biGRU, '
+                                   'attention head, clip_bce, backward, Adam-amsgrad), batch_size %d + mixup '
+                                   '= %d raw 32 kHz x 10 s clips per GPU per step' % (MODEL, bs, b2),
+                       'batch_size_per_gpu': bs, 'raw_clips_per_gpu_per_step': b2,
+                       'parallelism': 'dp%d, one NCCL all-reduce of the flat fp32 gradient per step' % world,
+                       'precision': 'bf16 tensor-core operands / activations, fp32 accumulation, fp32 front-end, '
+                                    'BN statistics, GRU, heads, loss, optimizer',
+                       'l2': 'inputs larger than L2 (waveforms %.0f MB per step, activations > 10 GB)'
+                             % (b2 * CLIP_SAMPLES * 4 / 1e6)},
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e / args.steps,
+                    'h2d_bytes_per_step': int(wave_host.numel() * 4 + target_host.numel() * 4 + b2 * 4),
+                    'd2h_bytes_per_step': 4, 'loss': stage.get('loss')},
+            'gpu_launches': launches,
+            'clocks': clock_info,
+            'roofline': roof,
+            'cpu_baseline': cpu,
+            'kernel_shares': shares,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=256, help='batch_size per GPU (raw clips = 2x under mixup)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # plain `python bench.py --gpus N`: re-launch ourselves under torchrun
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(args.gpus),
+               '--master-addr', '127.0.0.1', '--master-port', '29513', os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_ours(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -128,6 +128,9 @@ int sed_bn0_bwd_reduce(const float* dout, const float* logmel, const float* mean
 /* torchlibrosa.augmentation.SpecAugmentation.forward stand-alone (in place, (B,C,T,F) fp32). */
 int sed_spec_augment_f32(float* x, int B, int C, int T, int F, const int* t_stripes, int nt, const int* f_stripes,
                          int nf, sed_stream_t stream);
+/* pytorch_utils.do_mixup (pytorch_utils.py:80-93) on a small (B2, n) fp32 matrix -- the targets at
+ * main.py:246: out[i] = x[2i]*lam[2i] + x[2i+1]*lam[2i+1], out (B2/2, n). */
+int sed_mix_pairs_f32(const float* x, const float* lam, int B2, int n, float* out, sed_stream_t stream);
 int sed_reduce_partials(const float* partial, int P, long long n, float* out, int accumulate, float scale,
                         sed_stream_t stream);
 

@@ -43,6 +43,7 @@ SIGNATURES = {
     'sed_bn0_aug_mix_fwd': [P, P, P, P, I, P, I, P, I, I, I, P, P],
     'sed_bn0_bwd_reduce': [P, P, P, P, P, I, P, I, P, I, I, I, P, P],
     'sed_spec_augment_f32': [P, I, I, I, I, P, I, P, I, P],
+    'sed_mix_pairs_f32': [P, P, I, I, P, P],
     'sed_reduce_partials': [P, I, L, P, I, F, P],
     'sed_conv_c1_grid': [],
     'sed_conv_c1_fwd': [P, P, P, P, I, I, I, I, P],
@@ -95,9 +96,24 @@ def lib():
     return _lib
 
 
+# Optional per-entry-point device timing (bench.py's roofline leg / tools): when PROFILE is a list,
+# every call is bracketed by CUDA events on torch's current stream and (name, tag, start, end) is
+# appended; the caller synchronises and reads elapsed times.  None (default) = no overhead.
+PROFILE = None
+PROFILE_TAG = None
+
+
 def call(name, *args):
     fn = getattr(lib(), name)
-    status = fn(*args)
+    if PROFILE is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        status = fn(*args)
+        e1.record()
+        PROFILE.append((name, PROFILE_TAG, e0, e1))
+    else:
+        status = fn(*args)
     if status != 0:
         msg = lib().sed_last_error_string()
         raise RuntimeError('%s failed (status %d): %s' % (name, status, (msg or b'').decode()))

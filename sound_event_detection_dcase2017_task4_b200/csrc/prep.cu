@@ -136,6 +136,17 @@ __global__ void spec_augment_kernel(float* __restrict__ x, int B, int C, int T, 
   }
 }
 
+// do_mixup on a small (B2, n) fp32 matrix (the targets, main.py:246): out[i] = x[2i]*lam[2i] + x[2i+1]*lam[2i+1]
+__global__ void mix_pairs_kernel(const float* __restrict__ x, const float* __restrict__ lam, int Bout, int n,
+                                 float* __restrict__ out) {
+  const long long total = (long long)Bout * n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / n), c = (int)(i % n);
+    out[i] = x[(long long)(2 * b) * n + c] * lam[2 * b] + x[(long long)(2 * b + 1) * n + c] * lam[2 * b + 1];
+  }
+}
+
 // out[i] = sum over P partial rows (fp64 accumulate) -- generic deterministic second-level reduction
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int P, long long n, float* __restrict__ out,
                                        int accumulate, float scale) {
@@ -203,6 +214,17 @@ int sed_spec_augment_f32(float* x, int B, int C, int T, int F, const int* t_stri
   const int grid = (int)min((total + 255) / 256, (long long)sm_count() * 16);
   spec_augment_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, B, C, T, F, st);
   SED_LAUNCH_CHECK("spec_augment_kernel");
+  return 0;
+}
+
+int sed_mix_pairs_f32(const float* x, const float* lam, int B2, int n, float* out, sed_stream_t stream) {
+  SED_REQUIRE(x && lam && out, "sed_mix_pairs_f32: null pointer");
+  SED_REQUIRE(B2 % 2 == 0 && n >= 1, "sed_mix_pairs_f32: needs an even number of rows (got %d)", B2);
+  if (B2 == 0) return 0;
+  const long long total = (long long)(B2 / 2) * n;
+  const int grid = (int)min((total + 255) / 256, (long long)sm_count() * 8);
+  mix_pairs_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, lam, B2 / 2, n, out);
+  SED_LAUNCH_CHECK("mix_pairs_kernel");
   return 0;
 }
 

@@ -136,6 +136,17 @@ def spec_augment_(x, t_stripes, f_stripes):
     return x
 
 
+def mix_pairs(x, lam):
+    """do_mixup (pytorch_utils.py:80-93) of a (B2, n) fp32 matrix: the targets at main.py:246."""
+    x, lam = x.contiguous().float(), lam.contiguous().float()
+    b2 = x.shape[0]
+    n = x.numel() // max(b2, 1)
+    out = _empty((b2 // 2,) + tuple(x.shape[1:]), F32, x)
+    with _dev(x):
+        call('sed_mix_pairs_f32', x.data_ptr(), lam.data_ptr(), b2, n, out.data_ptr(), stream_of(x))
+    return out
+
+
 def reduce_partials(partial, out, scale=1.0, accumulate=False):
     P = partial.shape[0]
     n = partial.numel() // P
