@@ -11,9 +11,8 @@ from . import ops
 
 class _ConvBlockFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, block, x, ph, pw, w1, w2, g1, b1, g2, b2):
+    def forward(ctx, block, x, ph, pw, keep, w1, w2, g1, b1, g2, b2):
         training = block.training
-        keep = training and torch.is_grad_enabled()
         b, cin, h, w = x.shape
         if cin == 1:
             x_in = x.reshape(b, h, w).float().contiguous()
@@ -55,7 +54,7 @@ class _ConvBlockFn(torch.autograd.Function):
         if ctx.cin != 1:
             dx = dx.float().permute(0, 3, 1, 2)
         blk = l1
-        return (None, dx, None, None, grads.get(l1.conv.weight), grads.get(l2.conv.weight),
+        return (None, dx, None, None, None, grads.get(l1.conv.weight), grads.get(l2.conv.weight),
                 grads.get(l1.bn.weight), grads.get(l1.bn.bias), grads.get(l2.bn.weight), grads.get(l2.bn.bias))
 
 
@@ -70,7 +69,8 @@ def conv_block_forward(block, input, pool_size=(2, 2), pool_type='avg'):
     if not input.is_cuda:
         raise RuntimeError('ConvBlock: CUDA tensor required (no CPU path in this package)')
     ph, pw = pool_size
-    return _ConvBlockFn.apply(block, input, ph, pw, block.conv1.weight, block.conv2.weight, block.bn1.weight,
+    keep = block.training and torch.is_grad_enabled()
+    return _ConvBlockFn.apply(block, input, ph, pw, keep, block.conv1.weight, block.conv2.weight, block.bn1.weight,
                               block.bn1.bias, block.bn2.weight, block.bn2.bias)
 
 

@@ -1,0 +1,324 @@
+// attention.cu -- scaled-dot-product attention of the CNN-Transformer variants, forward and
+// backward, plus the dropout+ReLU that follows the output projection.
+//
+// Replaces ScaledDotProductAttention.forward (/root/reference/pytorch/models.py:596-608:
+// bmm, /temperature, Softmax(dim=2), Dropout(0.1), bmm) as called from MultiHead.forward
+// (models.py:641-665) including its four permute().contiguous() copies: heads are addressed in
+// place inside the (B*T, n_head*d) projection outputs, nothing is transposed or copied.
+// The 512->512 projections around it (w_qs/w_ks/w_vs/fc) are tensor-core GEMMs (sed_gemm_tc).
+//
+// One CTA per (batch, head); sequence length T <= 128 (125 for 10 s clips), head dim 64, fp32.
+//   forward : warp per query row: s = q.K^T/temp -> softmax -> (dropout) -> o = p.V
+//   backward: pass A, warp per query row: dP = dO.V^T -> dS -> dQ; dS rows to a scratch tile;
+//             pass B, warp per key row:   dK = dS^T.Q/temp, dV = Pd^T.dO
+// Dropout uses a counter-based Philox4x32-10 stream keyed by (seed, element index): the mask is
+// recomputed in the backward instead of being stored.  (Not bit-identical to torch's own Philox
+// usage -- parity tests run with dropout disabled or compare statistics)
+#include "common.cuh"
+
+namespace sed {
+namespace {
+
+constexpr int kD = 64;            // head dimension (d_k = d_v = 64, models.py:702-707)
+constexpr int kMaxT = 128;
+constexpr int kAttThreads = 256;
+constexpr int kWarps = kAttThreads / 32;
+constexpr int kLdK = kD + 1;      // padded row stride of the K / Q tile: conflict-free column walks
+
+__device__ __forceinline__ uint32_t mulhilo(uint32_t a, uint32_t b, uint32_t& hi) {
+  const unsigned long long p = (unsigned long long)a * b;
+  hi = (uint32_t)(p >> 32);
+  return (uint32_t)p;
+}
+// Philox4x32-10: 4 x 32 random bits for counter (idx >> 2); returns the (idx & 3)-th word.
+__device__ __forceinline__ uint32_t philox_word(unsigned long long seed, unsigned long long offset,
+                                                unsigned long long idx) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  const unsigned long long ctr = (idx >> 2) + offset;
+  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0x5ed5ed5eu, c3 = 0;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0, hi1;
+    const uint32_t lo0 = mulhilo(0xD2511F53u, c0, hi0);
+    const uint32_t lo1 = mulhilo(0xCD9E8D57u, c2, hi1);
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  const uint32_t w = (uint32_t)(idx & 3);
+  return w == 0 ? c0 : (w == 1 ? c1 : (w == 2 ? c2 : c3));
+}
+__device__ __forceinline__ bool keep_elem(unsigned long long seed, unsigned long long offset,
+                                          unsigned long long idx, float p) {
+  const float u = (float)(philox_word(seed, offset, idx) >> 8) * (1.0f / 16777216.0f);
+  return u >= p;
+}
+
+struct AttParams {
+  const float* q; const float* k; const float* v;   // (B*T, ld) row-major, head h at columns h*64
+  int ldq, ldk, ldv;
+  int B, T, H;
+  float inv_temp;
+  float p_drop;                                       // 0 = no dropout
+  unsigned long long seed, offset;
+};
+
+// ctx (B*T, H*64) fp32; probs (B, H, T, T) fp32 softmax output BEFORE dropout (may be nullptr)
+__global__ void __launch_bounds__(kAttThreads)
+attention_fwd_kernel(AttParams p, float* __restrict__ ctx, float* __restrict__ probs) {
+  extern __shared__ float smem[];
+  float* sK = smem;                         // [T][kLdK]
+  float* sV = sK + kMaxT * kLdK;            // [T][kD]
+  float* sQ = sV + kMaxT * kD;              // [kWarps][kD]
+  float* sP = sQ + kWarps * kD;             // [kWarps][kMaxT]
+  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const int T = p.T;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < T * kD; i += kAttThreads) {
+    const int t = i / kD, d = i % kD;
+    const long long row = (long long)b * T + t;
+    sK[t * kLdK + d] = p.k[row * p.ldk + h * kD + d];
+    sV[t * kD + d] = p.v[row * p.ldv + h * kD + d];
+  }
+  __syncthreads();
+  const float keep_scale = p.p_drop > 0.f ? 1.0f / (1.0f - p.p_drop) : 1.0f;
+  for (int i = warp; i < T; i += kWarps) {
+    const long long row = (long long)b * T + i;
+    sQ[warp * kD + lane] = p.q[row * p.ldq + h * kD + lane];
+    sQ[warp * kD + lane + 32] = p.q[row * p.ldq + h * kD + lane + 32];
+    __syncwarp();
+    float s[kMaxT / 32];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < kMaxT / 32; ++c) {
+      const int j = lane + 32 * c;
+      float a = 0.f;
+      if (j < T) {
+        const float* kr = sK + j * kLdK;
+        const float* qr = sQ + warp * kD;
+#pragma unroll 16
+        for (int d = 0; d < kD; ++d) a = fmaf(qr[d], kr[d], a);
+        a *= p.inv_temp;
+        mx = fmaxf(mx, a);
+      }
+      s[c] = a;
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxT / 32; ++c) {
+      const int j = lane + 32 * c;
+      s[c] = j < T ? expf(s[c] - mx) : 0.f;
+      sum += s[c];
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    const long long pbase = (((long long)b * p.H + h) * T + i) * T;
+#pragma unroll
+    for (int c = 0; c < kMaxT / 32; ++c) {
+      const int j = lane + 32 * c;
+      if (j < T) {
+        float pr = s[c] * inv;
+        if (probs) probs[pbase + j] = pr;
+        if (p.p_drop > 0.f) pr = keep_elem(p.seed, p.offset, (unsigned long long)(pbase + j), p.p_drop) ? pr * keep_scale : 0.f;
+        sP[warp * kMaxT + j] = pr;
+      }
+    }
+    __syncwarp();
+    float o0 = 0.f, o1 = 0.f;
+    const float* pr = sP + warp * kMaxT;
+    for (int j = 0; j < T; ++j) {
+      const float w = pr[j];
+      o0 = fmaf(w, sV[j * kD + lane], o0);
+      o1 = fmaf(w, sV[j * kD + lane + 32], o1);
+    }
+    ctx[row * (p.H * kD) + h * kD + lane] = o0;
+    ctx[row * (p.H * kD) + h * kD + lane + 32] = o1;
+    __syncwarp();
+  }
+}
+
+// dctx (B*T, H*64); probs (B,H,T,T) from the forward; ds_scratch (B,H,T,T);
+// dq/dk/dv written with the same addressing as q/k/v (ld = ldq/ldk/ldv).
+__global__ void __launch_bounds__(kAttThreads)
+attention_bwd_kernel(AttParams p, const float* __restrict__ dctx, const float* __restrict__ probs,
+                     float* __restrict__ ds_scratch, float* __restrict__ dq, float* __restrict__ dk,
+                     float* __restrict__ dv) {
+  extern __shared__ float smem[];
+  float* sA = smem;                         // pass A: K [T][kLdK]   pass B: Q  [T][kLdK]
+  float* sB = sA + kMaxT * kLdK;            // pass A: V [T][kLdK]   pass B: dO [T][kLdK]
+  float* sR = sB + kMaxT * kLdK;            // [kWarps][kD]   dO row
+  float* sS = sR + kWarps * kD;             // [kWarps][kMaxT] dS row
+  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const int T = p.T, HD = p.H * kD;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float keep_scale = p.p_drop > 0.f ? 1.0f / (1.0f - p.p_drop) : 1.0f;
+  const long long tile = ((long long)b * p.H + h) * T * T;
+  for (int i = threadIdx.x; i < T * kD; i += kAttThreads) {
+    const int t = i / kD, d = i % kD;
+    const long long row = (long long)b * T + t;
+    sA[t * kLdK + d] = p.k[row * p.ldk + h * kD + d];
+    sB[t * kLdK + d] = p.v[row * p.ldv + h * kD + d];
+  }
+  __syncthreads();
+  // ---- pass A: per query row
+  for (int i = warp; i < T; i += kWarps) {
+    const long long row = (long long)b * T + i;
+    sR[warp * kD + lane] = dctx[row * HD + h * kD + lane];
+    sR[warp * kD + lane + 32] = dctx[row * HD + h * kD + lane + 32];
+    __syncwarp();
+    float dp[kMaxT / 32], pr[kMaxT / 32];
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxT / 32; ++c) {
+      const int j = lane + 32 * c;
+      float a = 0.f, pj = 0.f;
+      if (j < T) {
+        const float* vr = sB + j * kLdK;
+        const float* dr = sR + warp * kD;
+#pragma unroll 16
+        for (int d = 0; d < kD; ++d) a = fmaf(dr[d], vr[d], a);
+        pj = probs[tile + (long long)i * T + j];
+        if (p.p_drop > 0.f)
+          a = keep_elem(p.seed, p.offset, (unsigned long long)(tile + (long long)i * T + j), p.p_drop) ? a * keep_scale : 0.f;
+        dot += a * pj;
+      }
+      dp[c] = a;
+      pr[c] = pj;
+    }
+    dot = warp_sum(dot);
+#pragma unroll
+    for (int c = 0; c < kMaxT / 32; ++c) {
+      const int j = lane + 32 * c;
+      if (j < T) {
+        const float ds = pr[c] * (dp[c] - dot) * p.inv_temp;      // already includes 1/temperature
+        sS[warp * kMaxT + j] = ds;
+        ds_scratch[tile + (long long)i * T + j] = ds;
+      }
+    }
+    __syncwarp();
+    float q0 = 0.f, q1 = 0.f;
+    const float* sr = sS + warp * kMaxT;
+    for (int j = 0; j < T; ++j) {
+      const float w = sr[j];
+      q0 = fmaf(w, sA[j * kLdK + lane], q0);
+      q1 = fmaf(w, sA[j * kLdK + lane + 32], q1);
+    }
+    dq[row * p.ldq + h * kD + lane] = q0;
+    dq[row * p.ldq + h * kD + lane + 32] = q1;
+    __syncwarp();
+  }
+  __syncthreads();                           // all dS rows of this tile written (same CTA reads them back)
+  for (int i = threadIdx.x; i < T * kD; i += kAttThreads) {
+    const int t = i / kD, d = i % kD;
+    const long long row = (long long)b * T + t;
+    sA[t * kLdK + d] = p.q[row * p.ldq + h * kD + d];
+    sB[t * kLdK + d] = dctx[row * HD + h * kD + d];
+  }
+  __syncthreads();
+  // ---- pass B: per key row
+  for (int j = warp; j < T; j += kWarps) {
+    float k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
+    for (int i = 0; i < T; ++i) {
+      const long long e = tile + (long long)i * T + j;
+      const float ds = ds_scratch[e];
+      float pd = probs[e];
+      if (p.p_drop > 0.f) pd = keep_elem(p.seed, p.offset, (unsigned long long)e, p.p_drop) ? pd * keep_scale : 0.f;
+      k0 = fmaf(ds, sA[i * kLdK + lane], k0);
+      k1 = fmaf(ds, sA[i * kLdK + lane + 32], k1);
+      v0 = fmaf(pd, sB[i * kLdK + lane], v0);
+      v1 = fmaf(pd, sB[i * kLdK + lane + 32], v1);
+    }
+    const long long row = (long long)b * T + j;
+    dk[row * p.ldk + h * kD + lane] = k0;
+    dk[row * p.ldk + h * kD + lane + 32] = k1;
+    dv[row * p.ldv + h * kD + lane] = v0;
+    dv[row * p.ldv + h * kD + lane + 32] = v1;
+  }
+}
+
+// y = relu(dropout_p(x)) elementwise (models.py:664: F.relu_(self.dropout(self.fc(output))))
+__global__ void dropout_relu_fwd_kernel(const float* __restrict__ x, long long n, float p, unsigned long long seed,
+                                        unsigned long long offset, float* __restrict__ y) {
+  const float keep_scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = x[i];
+    if (p > 0.f) v = keep_elem(seed, offset, (unsigned long long)i, p) ? v * keep_scale : 0.f;
+    y[i] = fmaxf(v, 0.f);
+  }
+}
+// dx = dy * [y > 0] / (1 - p): y > 0 implies the element was kept
+__global__ void dropout_relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, long long n, float p,
+                                        float* __restrict__ dx) {
+  const float keep_scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dx[i] = y[i] > 0.f ? dy[i] * keep_scale : 0.f;
+}
+
+int check_att(const char* name, const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, int B, int T,
+              int H, int d) {
+  SED_REQUIRE(q && k && v, "%s: null pointer", name);
+  SED_REQUIRE(d == kD, "%s: head dimension %d unsupported (64 only)", name, d);
+  SED_REQUIRE(T >= 1 && T <= kMaxT, "%s: sequence length %d out of range (1..%d)", name, T, kMaxT);
+  SED_REQUIRE(H >= 1 && ldq >= H * d && ldk >= H * d && ldv >= H * d, "%s: bad leading dimensions", name);
+  SED_REQUIRE(B >= 0, "%s: bad batch", name);
+  return 0;
+}
+
+}  // namespace
+}  // namespace sed
+
+using namespace sed;
+
+extern "C" {
+
+int sed_attention_fwd(const float* q, const float* k, const float* v, int ldq, int ldk, int ldv, int B, int T, int H,
+                      int d, float temperature, float p_drop, unsigned long long seed, unsigned long long offset,
+                      float* ctx, float* probs, sed_stream_t stream) {
+  if (int rc = check_att("sed_attention_fwd", q, k, v, ldq, ldk, ldv, B, T, H, d)) return rc;
+  SED_REQUIRE(ctx, "sed_attention_fwd: null output");
+  SED_REQUIRE(p_drop >= 0.f && p_drop < 1.f && temperature > 0.f, "sed_attention_fwd: bad scalars");
+  if (B == 0) return 0;
+  AttParams p{q, k, v, ldq, ldk, ldv, B, T, H, 1.0f / temperature, p_drop, seed, offset};
+  const size_t smem = sizeof(float) * (size_t)(kMaxT * kLdK + kMaxT * kD + kWarps * kD + kWarps * kMaxT);
+  SED_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  attention_fwd_kernel<<<B * H, kAttThreads, smem, (cudaStream_t)stream>>>(p, ctx, probs);
+  SED_LAUNCH_CHECK("attention_fwd_kernel");
+  return 0;
+}
+
+int sed_attention_bwd(const float* q, const float* k, const float* v, int ldq, int ldk, int ldv, int B, int T, int H,
+                      int d, float temperature, float p_drop, unsigned long long seed, unsigned long long offset,
+                      const float* dctx, const float* probs, float* ds_scratch, float* dq, float* dk, float* dv,
+                      sed_stream_t stream) {
+  if (int rc = check_att("sed_attention_bwd", q, k, v, ldq, ldk, ldv, B, T, H, d)) return rc;
+  SED_REQUIRE(dctx && probs && ds_scratch && dq && dk && dv, "sed_attention_bwd: null pointer");
+  if (B == 0) return 0;
+  AttParams p{q, k, v, ldq, ldk, ldv, B, T, H, 1.0f / temperature, p_drop, seed, offset};
+  const size_t smem = sizeof(float) * (size_t)(2 * kMaxT * kLdK + kWarps * kD + kWarps * kMaxT);
+  SED_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  attention_bwd_kernel<<<B * H, kAttThreads, smem, (cudaStream_t)stream>>>(p, dctx, probs, ds_scratch, dq, dk, dv);
+  SED_LAUNCH_CHECK("attention_bwd_kernel");
+  return 0;
+}
+
+int sed_dropout_relu_fwd(const float* x, long long n, float p_drop, unsigned long long seed, unsigned long long offset,
+                         float* y, sed_stream_t stream) {
+  SED_REQUIRE(x && y && n >= 0 && p_drop >= 0.f && p_drop < 1.f, "sed_dropout_relu_fwd: bad arguments");
+  if (n == 0) return 0;
+  const int grid = (int)min((n + 255) / 256, (long long)sm_count() * 16);
+  dropout_relu_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, p_drop, seed, offset, y);
+  SED_LAUNCH_CHECK("dropout_relu_fwd_kernel");
+  return 0;
+}
+
+int sed_dropout_relu_bwd(const float* dy, const float* y, long long n, float p_drop, float* dx, sed_stream_t stream) {
+  SED_REQUIRE(dy && y && dx && n >= 0 && p_drop >= 0.f && p_drop < 1.f, "sed_dropout_relu_bwd: bad arguments");
+  if (n == 0) return 0;
+  const int grid = (int)min((n + 255) / 256, (long long)sm_count() * 16);
+  dropout_relu_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, y, n, p_drop, dx);
+  SED_LAUNCH_CHECK("dropout_relu_bwd_kernel");
+  return 0;
+}
+
+}  // extern "C"

@@ -99,10 +99,22 @@ class LogmelFilterBank(nn.Module):
         if freeze_parameters:
             for p in self.parameters():
                 p.requires_grad = False
+        self._banks = {}        # device -> MelBankCSR; the dict object is shared by DataParallel replicas
+
+    def mel_bank(self):
+        return _fe.mel_bank_for(self.melW, self._banks)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._banks.clear()
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._banks.clear()
+        return super()._load_from_state_dict(*args, **kwargs)
 
     def forward(self, input):
         """(B, 1, T, 513) -> (B, 1, T, n_mels); fused with the STFT when fed by Spectrogram."""
-        bank = _fe.mel_bank_for(self.melW)
+        bank = self.mel_bank()
         if isinstance(input, LazyPowerSpectrogram) and input._dense is None and self.is_log:
             out = _fe.logmel(input._wave, input._hop, bank, amin=self.amin, ref=self.ref)
         else:

@@ -59,18 +59,19 @@ def _conv_layer(conv_mod, bn_mod, x_in, ph, pw, training, out_f32, keep):
     return out, lc
 
 
-def trunk_forward(model, wave, lam, training, stripes=None):
+def trunk_forward(model, wave, lam, training, stripes=None, keep=None):
     """waveform (B2, L) fp32/int16 -> features (B, T/8, 512) fp32 time-major, TrunkCtx.
 
     ``lam``: fp32 (B2,) mixup coefficients or None (models.py:210-211).  ``stripes``: optional
     pre-drawn (t, f) int32 tables; by default they are drawn here from the torch CPU generator
     in the reference's order whenever ``training`` is set (models.py:206-207)."""
     ctx = TrunkCtx()
+    keep = training if keep is None else keep       # save activations for trunk_backward
     ctx.training = training
     ctx.bn0 = model.bn0
     hop = model.spectrogram_extractor.stft.hop_length
     lmx = model.logmel_extractor
-    bank = fe.mel_bank_for(lmx.melW)
+    bank = lmx.mel_bank()
     logmel = fe.logmel(wave, hop, bank, amin=lmx.amin, ref=lmx.ref)           # (B2, 1, T, M)
     b2, _, t, m = logmel.shape
     logmel = logmel.view(b2, t, m)
@@ -91,17 +92,17 @@ def trunk_forward(model, wave, lam, training, stripes=None):
         st0 = ops.bn_eval_affine(model.bn0)
         ctx.t_stripes = ctx.f_stripes = ctx.lam = None
     x = ops.bn0_aug_mix_fwd(logmel, st0, ctx.t_stripes, ctx.f_stripes, ctx.lam)   # (B, T, M) fp32
-    ctx.logmel, ctx.st0, ctx.x0 = (logmel, st0, x) if training else (None, None, None)
+    ctx.logmel, ctx.st0, ctx.x0 = (logmel, st0, x) if keep else (None, None, None)
     ctx.layers = []
     blocks = (model.conv_block1, model.conv_block2, model.conv_block3, model.conv_block4)
     for bi, blk in enumerate(blocks):
         last = bi == len(blocks) - 1
-        x, lc = _conv_layer(blk.conv1, blk.bn1, x, 1, 1, training, False, training)
+        x, lc = _conv_layer(blk.conv1, blk.bn1, x, 1, 1, training, False, keep)
         ctx.layers.append(lc)
         wd = x.shape[2]
         # blocks 1-3: avg_pool 2x2; block 4: pool 1x1 then mean over the 8 remaining mel bins
         ph, pw = (1, wd) if last else (2, 2)
-        x, lc = _conv_layer(blk.conv2, blk.bn2, x, ph, pw, training, last, training)
+        x, lc = _conv_layer(blk.conv2, blk.bn2, x, ph, pw, training, last, keep)
         ctx.layers.append(lc)
     b, tp, one, c = x.shape
     return x.view(b, tp, c), ctx

@@ -6,7 +6,6 @@ constructed at /root/reference/pytorch/models.py:166-173 and called at :199-200.
 """
 import math
 import threading
-import weakref
 
 import numpy as np
 import torch
@@ -85,21 +84,34 @@ class MelBankCSR(object):
 
 
 _csr_lock = threading.Lock()
-_csr_cache = weakref.WeakKeyDictionary()     # melW tensor -> (version, device, MelBankCSR)
 
 
-def mel_bank_for(melW):
-    """Cached CSR bank for a melW parameter; rebuilt if the tensor was modified or moved.
-    Keyed on the tensor object (not on ``self``) so DataParallel replicas each get their own
-    per-device copy."""
-    key = melW
-    with _csr_lock:
-        hit = _csr_cache.get(key)
-        if hit is not None and hit[0] == melW._version and hit[1] == melW.device:
-            return hit[2]
-    bank = MelBankCSR(melW)
-    with _csr_lock:
-        _csr_cache[key] = (melW._version, melW.device, bank)
+def mel_bank_for(melW, shared=None):
+    """Cached CSR bank for a melW parameter.
+
+    First level: an attribute on the tensor object itself, valid while (version, device) match --
+    the steady state of a single-device model (same Parameter object every step).
+    Second level (``shared``: a dict owned by the LogmelFilterBank module and therefore shared by
+    DataParallel's shallow-copied replicas, whose parameters are fresh tensors every forward):
+    one bank per device for FROZEN parameters; the owning module clears it whenever its
+    parameters are reloaded or moved (load_state_dict / .to())."""
+    hit = getattr(melW, '_sed_bank', None)
+    if hit is not None and hit[0] == melW._version and hit[1] == melW.device:
+        return hit[2]
+    bank = None
+    use_shared = shared is not None and not melW.requires_grad
+    if use_shared:
+        with _csr_lock:
+            bank = shared.get(melW.device)
+    if bank is None:
+        bank = MelBankCSR(melW)
+        if use_shared:
+            with _csr_lock:
+                shared[melW.device] = bank
+    try:
+        melW._sed_bank = (melW._version, melW.device, bank)
+    except Exception:
+        pass
     return bank
 
 

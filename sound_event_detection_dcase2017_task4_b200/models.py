@@ -151,10 +151,9 @@ class _SedFunction(torch.autograd.Function):
     backward: d clipwise -> gradients of every trainable parameter."""
 
     @staticmethod
-    def forward(ctx, model, wave, lam, n_params, *params):
-        training = model.training
-        need_grad = training and torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        feat, tctx = engine.trunk_forward(model, wave, lam if training else None, training)
+    def forward(ctx, model, wave, lam, need_grad, *params):
+        training = model.training          # (grad mode is always off inside Function.forward)
+        feat, tctx = engine.trunk_forward(model, wave, lam if training else None, training, keep=need_grad)
         feat, mctx = temporal.forward(model, feat, training, keep=need_grad)
         out, hctx = engine.head_forward(model, feat, model.interpolate_ratio, want_frame=True, keep=need_grad)
         ctx.model, ctx.params = model, params
@@ -234,7 +233,8 @@ class _Cnn9(nn.Module):
             raise RuntimeError('%s: CUDA tensors required -- this package has no CPU path'
                                % type(self).__name__)
         params = [p for p in self.parameters() if p.requires_grad]
-        clip, frame, emb = _SedFunction.apply(self, input, mixup_lambda, len(params), *params)
+        need_grad = self.training and torch.is_grad_enabled() and len(params) > 0
+        clip, frame, emb = _SedFunction.apply(self, input, mixup_lambda, need_grad, *params)
         return {'framewise_output': frame, 'clipwise_output': clip, 'embedding': emb}
 
 
