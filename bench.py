@@ -235,17 +235,28 @@ def run_ours(args):
         lam_dev.copy_(lam_host, non_blocking=True)      # 2 KB of lambdas: host-generated in the reference too
         trainer.step(wave_dev, target_dev, lam_dev)
 
-    stage = {}
+    stage = {'slot': 0}
+    from sound_event_detection_dcase2017_task4_b200.feed import DeviceFeed
+    feed = DeviceFeed(dev, slots=2)
+    lam_slots = [torch.empty(b2, dtype=torch.float32).pin_memory() for _ in range(2)]
+
+    def submit(slot):
+        """Step inputs: waveforms + targets + this step's mixup lambdas, pinned host -> device slot."""
+        lam_slots[slot].copy_(torch.from_numpy(lam_gen.get_lambda(b2).astype(np.float32)))
+        feed.submit(slot, {'waveform': wave_host, 'target': target_host, 'lam': lam_slots[slot]})
 
     def step_e2e():
-        next_lambda()
-        w = wave_host.to(dev, non_blocking=True)
-        t = target_host.to(dev, non_blocking=True)
-        lam_dev.copy_(lam_host, non_blocking=True)
-        loss = trainer.step(w, t, lam_dev)
+        """One iteration of main.py:233-258 with HOST inputs: every step copies its own batch (on the copy
+        stream, overlapped with the previous step's kernels) and reads its loss back (main.py:253 prints it)."""
+        cur = stage['slot']
+        submit(cur ^ 1)                                  # next step's batch: H2D in flight during this step
+        batch = feed.acquire(cur)
+        loss = trainer.step(batch['waveform'], batch['target'], batch['lam'])
+        feed.release(cur)
         loss_host.copy_(loss, non_blocking=True)
-        torch.cuda.current_stream().synchronize()       # main.py:253 prints the loss every step
+        torch.cuda.current_stream().synchronize()
         stage['loss'] = float(loss_host)
+        stage['slot'] = cur ^ 1
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
@@ -254,7 +265,8 @@ def run_ours(args):
         clocks.start()
     ms, launches = timed(step_resident, args.steps)
     clock_info = clocks.stop() if rank == 0 else None
-    for _ in range(2):
+    submit(0)                                            # prologue: first batch (its copy is outside the timed region;
+    for _ in range(2):                                   #  each timed step issues exactly one batch copy)
         step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)
 
@@ -321,7 +333,8 @@ def run_ours(args):
                              % (b2 * CLIP_SAMPLES * 4 / 1e6)},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e / args.steps,
                     'h2d_bytes_per_step': int(wave_host.numel() * 4 + target_host.numel() * 4 + b2 * 4),
-                    'd2h_bytes_per_step': 4, 'loss': stage.get('loss')},
+                    'd2h_bytes_per_step': 4, 'loss': stage.get('loss'),
+                    'overlap': 'batch i+1 copied on a copy stream while step i computes (feed.DeviceFeed)'},
             'gpu_launches': launches,
             'clocks': clock_info,
             'roofline': roof,

@@ -189,6 +189,24 @@ int sed_gru_fwd(const float* gx, const float* w_hh, const float* b_hh, float* ou
 int sed_gru_bwd(const float* dout, const float* out, const float* gates, const float* w_hh, float* carry,
                 float* dgx, float* dgh, float* hprev, int B, int T, int H, sed_stream_t stream);
 
+/* ---- scaled-dot-product attention of MultiHead (pytorch/models.py:596-608 inside :641-665) -------
+ * q/k/v: fp32 (B*T, ld) row-major, head h in columns [h*64, h*64+64): the outputs of the w_qs / w_ks /
+ * w_vs projections used in place (replaces the four permute().contiguous() copies).  T <= 128, d = 64.
+ * ctx (B*T, H*64); probs (B,H,T,T) = softmax before dropout (saved for the backward, may be NULL).
+ * Dropout(p_drop) on the probabilities from Philox4x32-10(seed, offset + element/4); p_drop = 0 in eval.
+ * bwd: ds_scratch (B,H,T,T) workspace; dq/dk/dv use the addressing of q/k/v. */
+int sed_attention_fwd(const float* q, const float* k, const float* v, int ldq, int ldk, int ldv, int B, int T, int H,
+                      int d, float temperature, float p_drop, unsigned long long seed, unsigned long long offset,
+                      float* ctx, float* probs, sed_stream_t stream);
+int sed_attention_bwd(const float* q, const float* k, const float* v, int ldq, int ldk, int ldv, int B, int T, int H,
+                      int d, float temperature, float p_drop, unsigned long long seed, unsigned long long offset,
+                      const float* dctx, const float* probs, float* ds_scratch, float* dq, float* dk, float* dv,
+                      sed_stream_t stream);
+/* y = relu(dropout_p(x)) (models.py:664) and its backward dx = dy * [y > 0] / (1 - p). */
+int sed_dropout_relu_fwd(const float* x, long long n, float p_drop, unsigned long long seed, unsigned long long offset,
+                         float* y, sed_stream_t stream);
+int sed_dropout_relu_bwd(const float* dy, const float* y, long long n, float p_drop, float* dx, sed_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_PKG_DIR, 'libsedb200.so')
 
 _c_int, _c_ll, _c_float, _c_void_p = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_void_p
 P, I, L, F, D = _c_void_p, _c_int, _c_ll, _c_float, ctypes.c_double
+U = ctypes.c_ulonglong
 
 # name -> argtypes (all return int unless listed in _RESTYPES)
 SIGNATURES = {
@@ -65,6 +66,10 @@ SIGNATURES = {
     'sed_colsum_f32': [P, L, I, P, P],
     'sed_gru_fwd': [P, P, P, P, P, I, I, I, P],
     'sed_gru_bwd': [P, P, P, P, P, P, P, P, I, I, I, P],
+    'sed_attention_fwd': [P, P, P, I, I, I, I, I, I, I, F, F, U, U, P, P, P],
+    'sed_attention_bwd': [P, P, P, I, I, I, I, I, I, I, F, F, U, U, P, P, P, P, P, P, P],
+    'sed_dropout_relu_fwd': [P, L, F, U, U, P, P],
+    'sed_dropout_relu_bwd': [P, P, L, F, P, P],
     'sed_adam_amsgrad': [P, P, P, P, P, L, F, F, F, F, I, F, P],
 }
 _RESTYPES = {

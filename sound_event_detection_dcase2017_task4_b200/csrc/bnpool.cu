@@ -245,6 +245,200 @@ __global__ void bn_relu_pool_bwd_apply_kernel(const __nv_bfloat16* __restrict__ 
   }
 }
 
+// ================================================================ row-structured fast paths
+// Used when 256 % (C/8) == 0 and the pooling is 1x1 or 2x2 with even W: a CTA walks image rows,
+// thread t always owns channel octet t % (C/8), so every per-channel constant lives in registers
+// for the whole kernel and the inner loop has no integer division.  All accesses are 16-byte
+// vectors, several independent loads in flight per thread.
+constexpr int kRowThreads = 256;
+
+__device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void unpack8(const uint4& raw, float (&v)[8]) {
+  float2 a = unpack_bf16x2(raw.x), b = unpack_bf16x2(raw.y), c = unpack_bf16x2(raw.z), d = unpack_bf16x2(raw.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+
+// out row (b, ho) <- relu(bn(y rows ho*P .. ho*P+P-1)), P = 1 or 2 (square pool), bf16 out
+template <int kPool>
+__global__ void __launch_bounds__(kRowThreads, 4)
+bn_relu_pool_fwd_rows_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                             const float* __restrict__ shift, int B, int H, int W, int C,
+                             __nv_bfloat16* __restrict__ out) {
+  const int CV = C >> 3, Ho = H / kPool, Wo = W / kPool;
+  const int cv = threadIdx.x % CV, cv_shift = __ffs(CV) - 1;
+  float sc[8], sh[8];
+  load8f(scale + cv * 8, sc);
+  load8f(shift + cv * 8, sh);
+  const int out_vecs = Wo * CV;                    // vectors per output row
+  const long long in_row = (long long)W * C;       // elements per input row
+  const int rows = B * Ho;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int b = row / Ho, ho = row - b * Ho;
+    const __nv_bfloat16* src = y + ((long long)b * H + (long long)ho * kPool) * in_row;
+    __nv_bfloat16* dst = out + (long long)row * Wo * C;
+#pragma unroll 2
+    for (int v = threadIdx.x; v < out_vecs; v += kRowThreads) {
+      const int wo = v >> cv_shift;                  // CV divides 256 => power of two
+      uint4 raw[kPool * kPool];
+#pragma unroll
+      for (int dh = 0; dh < kPool; ++dh)
+#pragma unroll
+        for (int dw = 0; dw < kPool; ++dw)
+          raw[dh * kPool + dw] = ldg16(src + dh * in_row + ((long long)(wo * kPool + dw) * CV + cv) * 8);
+      float acc[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+      for (int i = 0; i < kPool * kPool; ++i) {
+        float x[8];
+        unpack8(raw[i], x);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += fmaxf(fmaf(x[k], sc[k], sh[k]), 0.f);
+      }
+      if (kPool == 2) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] *= 0.25f;
+      }
+      store8(dst + (long long)v * 8, acc);
+    }
+  }
+}
+
+// backward pass 1 over input rows (b, h): partial sums of g and g*xhat per channel
+template <int kPool, bool kGradF32>
+__global__ void __launch_bounds__(kRowThreads, 3)
+bn_bwd_reduce_rows_kernel(const __nv_bfloat16* __restrict__ y, const void* __restrict__ dA_,
+                          const float* __restrict__ scale, const float* __restrict__ shift,
+                          const float* __restrict__ mean, const float* __restrict__ invstd, int B, int H, int W,
+                          int C, float* __restrict__ partial) {
+  extern __shared__ float s_red[];                 // [lanes][2*C]
+  const int CV = C >> 3, Ho = H / kPool, Wo = W / kPool;
+  const int cv = threadIdx.x % CV, pl = threadIdx.x / CV, lanes = kRowThreads / CV, cv_shift = __ffs(CV) - 1;
+  float sc[8], sh[8], mu[8], is[8], sg[8], sgx[8];
+  load8f(scale + cv * 8, sc);
+  load8f(shift + cv * 8, sh);
+  load8f(mean + cv * 8, mu);
+  load8f(invstd + cv * 8, is);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sg[k] = sgx[k] = 0.f;
+  const int in_vecs = W * CV;
+  const int rows = B * H;
+  const float inv = kPool == 2 ? 0.25f : 1.0f;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int b = row / H, h = row - b * H;
+    const int ho = h / kPool;
+    if (ho >= Ho) continue;                          // floor-mode tail row: no gradient
+    const __nv_bfloat16* yrow = y + (long long)row * W * C;
+    const long long drow = ((long long)b * Ho + ho) * Wo * C;
+#pragma unroll 2
+    for (int v = threadIdx.x; v < in_vecs; v += kRowThreads) {
+      const int w = v >> cv_shift, wo = w / kPool;
+      if (wo >= Wo) continue;
+      const uint4 raw = ldg16(yrow + (long long)v * 8);
+      float g[8], x[8];
+      const long long o = drow + ((long long)wo * CV + cv) * 8;
+      if (kGradF32) load8f(reinterpret_cast<const float*>(dA_) + o, g);
+      else { const uint4 graw = ldg16(reinterpret_cast<const __nv_bfloat16*>(dA_) + o); unpack8(graw, g); }
+      unpack8(raw, x);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float act = fmaf(x[k], sc[k], sh[k]);
+        const float gk = act > 0.f ? g[k] * inv : 0.f;
+        sg[k] += gk;
+        sgx[k] += gk * (x[k] - mu[k]) * is[k];
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    s_red[pl * 2 * C + cv * 8 + k] = sg[k];
+    s_red[pl * 2 * C + C + cv * 8 + k] = sgx[k];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += kRowThreads) {
+    float a = 0.f;
+    for (int l = 0; l < lanes; ++l) a += s_red[l * 2 * C + i];
+    partial[(long long)blockIdx.x * 2 * C + i] = a;
+  }
+}
+
+// backward pass 2: dY = A*g + Bc*y + Cc for active elements (g = unpooled dA * 1/P^2 * relu mask)
+//   A = gamma*invstd, Bc = -A*mean(g*xhat)*invstd, Cc = -A*mean(g) - Bc*mean     (from coef, see finalize)
+template <int kPool, bool kGradF32>
+__global__ void __launch_bounds__(kRowThreads, 3)
+bn_bwd_apply_rows_kernel(const __nv_bfloat16* __restrict__ y, const void* __restrict__ dA_,
+                         const float* __restrict__ scale, const float* __restrict__ shift,
+                         const float* __restrict__ mean, const float* __restrict__ invstd,
+                         const float* __restrict__ coef, int B, int H, int W, int C,
+                         __nv_bfloat16* __restrict__ dy) {
+  const int CV = C >> 3, Ho = H / kPool, Wo = W / kPool;
+  const int cv = threadIdx.x % CV, cv_shift = __ffs(CV) - 1;
+  float sc[8], sh[8], cA[8], cB[8], cC[8];
+  {
+    float mu[8], is[8], c1[8], c2[8], c3[8];
+    load8f(scale + cv * 8, sc);
+    load8f(shift + cv * 8, sh);
+    load8f(mean + cv * 8, mu);
+    load8f(invstd + cv * 8, is);
+    load8f(coef + cv * 8, c1);
+    load8f(coef + C + cv * 8, c2);
+    load8f(coef + 2 * C + cv * 8, c3);
+    const float inv = kPool == 2 ? 0.25f : 1.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      cA[k] = c1[k] * inv;
+      cB[k] = -c1[k] * c3[k] * is[k];
+      cC[k] = -c1[k] * c2[k] - cB[k] * mu[k];
+    }
+  }
+  const int in_vecs = W * CV;
+  const int rows = B * H;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int b = row / H, h = row - b * H;
+    const int ho = h / kPool;
+    const bool row_in = ho < Ho;
+    const __nv_bfloat16* yrow = y + (long long)row * W * C;
+    __nv_bfloat16* orow = dy + (long long)row * W * C;
+    const long long drow = ((long long)b * Ho + (row_in ? ho : 0)) * Wo * C;
+#pragma unroll 2
+    for (int v = threadIdx.x; v < in_vecs; v += kRowThreads) {
+      const int w = v >> cv_shift, wo = w / kPool;
+      const bool inside = row_in && wo < Wo;
+      const uint4 raw = ldg16(yrow + (long long)v * 8);
+      float g[8], x[8], o[8];
+      if (inside) {
+        const long long oi = drow + ((long long)wo * CV + cv) * 8;
+        if (kGradF32) load8f(reinterpret_cast<const float*>(dA_) + oi, g);
+        else { const uint4 graw = ldg16(reinterpret_cast<const __nv_bfloat16*>(dA_) + oi); unpack8(graw, g); }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] = 0.f;
+      }
+      unpack8(raw, x);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float act = fmaf(x[k], sc[k], sh[k]);
+        const float gk = act > 0.f ? g[k] : 0.f;
+        o[k] = fmaf(cA[k], gk, fmaf(cB[k], x[k], cC[k]));
+      }
+      store8(orow + (long long)v * 8, o);
+    }
+  }
+}
+
+bool rows_path_ok(int H, int W, int C, int ph, int pw) {
+  const int CV = C / 8;
+  if (C % 8 != 0 || CV < 1 || CV > kRowThreads || kRowThreads % CV != 0) return false;
+  if (ph == 1 && pw == 1) return true;
+  return ph == 2 && pw == 2 && W % 2 == 0 && H >= 2;
+}
+// one full wave: `per_sm` CTAs of 256 threads are co-resident per SM (set by __launch_bounds__), so every
+// CTA walks the same number of rows and there is no partial second wave
+int rows_grid(int rows, int per_sm) {
+  const int cap = sm_count() * per_sm;
+  return rows < cap ? (rows < 1 ? 1 : rows) : cap;
+}
+
 int ew_grid(long long total, int threads) {
   long long g = (total + threads - 1) / threads;
   const long long cap = (long long)sm_count() * 16;
@@ -289,6 +483,14 @@ int sed_bn_relu_pool_fwd(const void* y, const float* scale, const float* shift, 
   const long long total = (long long)B * (H / ph) * (W / pw) * (C / 8);
   const int grid = ew_grid(total, 256);
   const __nv_bfloat16* yy = reinterpret_cast<const __nv_bfloat16*>(y);
+  if (!out_is_f32 && rows_path_ok(H, W, C, ph, pw) && (long long)B * H < (1LL << 31)) {
+    __nv_bfloat16* oo = reinterpret_cast<__nv_bfloat16*>(out);
+    const int g = rows_grid(B * (H / ph), 4);
+    if (ph == 1) bn_relu_pool_fwd_rows_kernel<1><<<g, kRowThreads, 0, (cudaStream_t)stream>>>(yy, scale, shift, B, H, W, C, oo);
+    else bn_relu_pool_fwd_rows_kernel<2><<<g, kRowThreads, 0, (cudaStream_t)stream>>>(yy, scale, shift, B, H, W, C, oo);
+    SED_LAUNCH_CHECK("bn_relu_pool_fwd_rows_kernel");
+    return 0;
+  }
   if (out_is_f32)
     bn_relu_pool_fwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(yy, scale, shift, B, H, W, C, ph, pw, out);
   else
@@ -299,7 +501,7 @@ int sed_bn_relu_pool_fwd(const void* y, const float* scale, const float* shift, 
 
 int sed_bn_bwd_partials(int C) {   // rows of the partial workspace used by the reduce pass
   (void)C;
-  return sm_count() * 4;
+  return sm_count() * 3;           // = one resident wave of the row-structured reduce kernel (3 CTAs / SM)
 }
 
 int sed_bn_relu_pool_bwd_reduce(const void* y, const void* dA, int grad_is_f32, const float* scale,
@@ -311,6 +513,15 @@ int sed_bn_relu_pool_bwd_reduce(const void* y, const void* dA, int grad_is_f32, 
   const int lanes = 256 / (C / 8);
   const size_t smem = (size_t)lanes * 2 * C * sizeof(float);
   const __nv_bfloat16* yy = reinterpret_cast<const __nv_bfloat16*>(y);
+  if (rows_path_ok(H, W, C, ph, pw) && (long long)B * H < (1LL << 31)) {
+    cudaStream_t st = (cudaStream_t)stream;
+#define SED_RED(P, F) bn_bwd_reduce_rows_kernel<P, F><<<grid, kRowThreads, smem, st>>>(yy, dA, scale, shift, mean, invstd, B, H, W, C, partial)
+    if (ph == 1) { if (grad_is_f32) SED_RED(1, true); else SED_RED(1, false); }
+    else { if (grad_is_f32) SED_RED(2, true); else SED_RED(2, false); }
+#undef SED_RED
+    SED_LAUNCH_CHECK("bn_bwd_reduce_rows_kernel");
+    return 0;
+  }
   if (grad_is_f32)
     bn_relu_pool_bwd_reduce_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(yy, dA, scale, shift, mean, invstd,
                                                                                     B, H, W, C, ph, pw, partial);
@@ -340,6 +551,16 @@ int sed_bn_relu_pool_bwd_apply(const void* y, const void* dA, int grad_is_f32, c
   const int grid = ew_grid(total, 256);
   const __nv_bfloat16* yy = reinterpret_cast<const __nv_bfloat16*>(y);
   __nv_bfloat16* dd = reinterpret_cast<__nv_bfloat16*>(dy);
+  if (rows_path_ok(H, W, C, ph, pw) && (long long)B * H < (1LL << 31)) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int g = rows_grid(B * H, 3);
+#define SED_APP(P, F) bn_bwd_apply_rows_kernel<P, F><<<g, kRowThreads, 0, st>>>(yy, dA, scale, shift, mean, invstd, coef, B, H, W, C, dd)
+    if (ph == 1) { if (grad_is_f32) SED_APP(1, true); else SED_APP(1, false); }
+    else { if (grad_is_f32) SED_APP(2, true); else SED_APP(2, false); }
+#undef SED_APP
+    SED_LAUNCH_CHECK("bn_bwd_apply_rows_kernel");
+    return 0;
+  }
   if (grad_is_f32)
     bn_relu_pool_bwd_apply_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(yy, dA, scale, shift, mean, invstd,
                                                                                 coef, B, H, W, C, ph, pw, dd);

@@ -77,7 +77,7 @@ __global__ void bn0_aug_mix_fwd_kernel(const float* __restrict__ x, const float*
       const long long per = (long long)T * M;
       float a0 = masked(st, c0, t, m) ? 0.f : fmaf(x[c0 * per + (long long)t * M + m], sc, sh);
       float a1 = masked(st, c1, t, m) ? 0.f : fmaf(x[c1 * per + (long long)t * M + m], sc, sh);
-      out[i] = a0 * lam[c0] + a1 * lam[c1];
+      out[i] = __fadd_rn(__fmul_rn(a0, lam[c0]), __fmul_rn(a1, lam[c1]));
     } else {
       out[i] = masked(st, b, t, m) ? 0.f : fmaf(x[i], sc, sh);
     }
@@ -143,7 +143,8 @@ __global__ void mix_pairs_kernel(const float* __restrict__ x, const float* __res
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int b = (int)(i / n), c = (int)(i % n);
-    out[i] = x[(long long)(2 * b) * n + c] * lam[2 * b] + x[(long long)(2 * b + 1) * n + c] * lam[2 * b + 1];
+    // separate roundings (no FMA contraction): bit-identical to torch's mul, mul, add
+    out[i] = __fadd_rn(__fmul_rn(x[(long long)(2 * b) * n + c], lam[2 * b]), __fmul_rn(x[(long long)(2 * b + 1) * n + c], lam[2 * b + 1]));
   }
 }
 

@@ -159,6 +159,8 @@ class _SedFunction(torch.autograd.Function):
         ctx.model, ctx.params = model, params
         ctx.saved = (tctx, mctx, hctx) if need_grad else None
         frame, emb = out['framewise_output'], out['embedding']
+        if model.temporal_kind == 'mha':
+            emb = feat.transpose(1, 2)          # models.py:838: the Transformer variants return the MHA output
         ctx.mark_non_differentiable(frame, emb)
         return out['clipwise_output'], frame, emb
 

@@ -29,6 +29,9 @@ for w in $WHAT; do
     kbench)
       timeout 600 python tools/bench_kernels.py --batch 64 > gpurun_out/kbench.log 2>&1
       echo "kbench exit $?" | tee -a gpurun_out/summary.txt; tail -40 gpurun_out/kbench.log;;
+    kbench256)
+      timeout 600 python tools/bench_kernels.py --batch 256 --what conv > gpurun_out/kbench256.log 2>&1
+      echo "kbench256 exit $?" | tee -a gpurun_out/summary.txt; tail -40 gpurun_out/kbench256.log;;
     bench)
       timeout 900 python bench.py > gpurun_out/bench.log 2>&1
       echo "bench exit $?" | tee -a gpurun_out/summary.txt; tail -5 gpurun_out/bench.log;;
