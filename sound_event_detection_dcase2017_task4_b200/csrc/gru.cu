@@ -15,8 +15,6 @@
 //   * BPTT: per step ONE launch; CTA = (direction, 16 batch rows, 32 columns of W_hh); the gate
 //     gradients of the 16 rows are rebuilt in shared memory, then dh_prev = dgh . W_hh (+ dh * z).
 //   * weight gradients after the loop: tensor-core TN GEMMs (sed_gemm_tn_tc) over all (b, t).
-#include <cooperative_groups.h>
-
 #include "common.cuh"
 
 namespace sed {
@@ -150,32 +148,56 @@ gru_bwd_step_kernel(const float* __restrict__ dout, const float* __restrict__ ou
   carry_out[((long long)d * B + b) * H + k0 + kl] = acc + sC[bl * kHT + kl];
 }
 
-// ================================================================ persistent cluster kernels (H = 256)
+// ================================================================ persistent kernels (H = 256)
 // The per-step kernels above re-read their W_hh slice from L2 at every time step (98 KB x 256 CTAs
 // x 125 steps) and pay a launch per step.  For the reference configuration (hidden size 256) the whole
-// recurrence instead runs in ONE launch: a thread-block cluster of 8 CTAs owns (32 batch rows, one
-// direction); CTA r of the cluster keeps the 96 x 256 slice of W_hh for hidden units [32r, 32r+32) in
-// shared memory for all T steps, computes its 32 x 32 block of h_t, and pushes it into the shared memory
-// of all 8 CTAs through DSMEM; one cluster barrier per time step replaces the kernel boundary.
-// Accumulation order per output is the same as in the step kernel (bit-identical results).
-namespace cg = cooperative_groups;
-
+// recurrence instead runs in ONE cooperative launch: a group of 8 CTAs owns (32 batch rows, one direction);
+// CTA r of the group keeps the slice of W_hh for hidden units [32r, 32r+32) in shared memory for all T
+// steps.  The groups exchange one time step through L2 (the `out` / `dGh` tensors that have to be written
+// anyway) and meet at a per-group arrive/wait counter in global memory.  (A thread-block-cluster version
+// with DSMEM exchange was measured first: only 8 clusters of 8 CTAs x 164 KB are co-resident on a B200, which
+// leaves more than half of the SMs idle -- profiles/r01_gru_cluster.md -- so the group barrier lives in L2.)
+// Accumulation order per output is the same as in the step kernels (bit-identical forward results).
 constexpr int kPH = 256;           // hidden size handled by the persistent kernels
-constexpr int kPB = 32;            // batch rows per cluster
-constexpr int kPJ = 32;            // hidden units (fwd) / W_hh columns (bwd) per CTA
-constexpr int kPCluster = kPH / kPJ;   // 8
+constexpr int kPB = 32;            // batch rows per group
+constexpr int kPJ = 32;            // hidden units per CTA
+constexpr int kPGroup = kPH / kPJ; // 8 CTAs per group
 constexpr int kPThreads = 256;
 constexpr int kPLdW = kPH + 4;
 
-__global__ void __cluster_dims__(kPCluster, 1, 1) __launch_bounds__(kPThreads, 1)
+// All CTAs of a group arrive; everyone leaves once `target` arrivals have been counted.  Writes made by any
+// thread of the CTA before the call are visible to every thread of the group after it (bar.sync, then
+// thread 0: fence + atomic + acquire spin, then bar.sync -- the cooperative-groups grid.sync pattern).
+__device__ __forceinline__ void group_barrier(unsigned int* ctr, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    unsigned int v;
+    unsigned int spins = 0;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      if (++spins > (1u << 28)) { printf("sed: GRU group barrier timed out\n"); __trap(); }
+    } while (v < target);
+  }
+  __syncthreads();
+}
+
+struct GruPersist {
+  unsigned int* sync_ctr;   // [tiles][2] arrive counters (zeroed by the host entry point)
+  int B, T, b_base;
+};
+
+__global__ void __launch_bounds__(kPThreads, 1)
 gru_fwd_persistent_kernel(const float* __restrict__ Gx, const float* __restrict__ Whh, const float* __restrict__ bhh,
-                          float* __restrict__ out, float* __restrict__ gates, int B, int T) {
+                          float* out, float* __restrict__ gates, GruPersist q) {
   extern __shared__ __align__(16) float smem[];
   float* sW = smem;                              // [3*kPJ][kPLdW]
-  float* sH = smem + 3 * kPJ * kPLdW;            // [2][kPB][kPH]
-  cg::cluster_group cluster = cg::this_cluster();
+  float* sH = smem + 3 * kPJ * kPLdW;            // [kPB][kPH]   h_{t-1} of this group's rows
   constexpr int H = kPH;
-  const int j0 = blockIdx.x * kPJ, b0 = blockIdx.y * kPB, d = blockIdx.z;
+  const int B = q.B, T = q.T;
+  const int j0 = blockIdx.x * kPJ, b0 = q.b_base + blockIdx.y * kPB, d = blockIdx.z;
+  unsigned int* ctr = q.sync_ctr + (blockIdx.y * 2 + d);
   const int tid = threadIdx.x;
   const float* W = Whh + (long long)d * 3 * H * H;
   for (int i = tid; i < 3 * kPJ * (H / 4); i += kPThreads) {
@@ -184,7 +206,6 @@ gru_fwd_persistent_kernel(const float* __restrict__ Gx, const float* __restrict_
     *reinterpret_cast<float4*>(sW + row * kPLdW + k4 * 4) =
         *reinterpret_cast<const float4*>(W + ((long long)(g * H + j0 + jl)) * H + k4 * 4);
   }
-  for (int i = tid; i < kPB * H; i += kPThreads) sH[i] = 0.f;      // h_0 = 0
   const int jl = tid & 31, bl0 = (tid >> 5) * 4;                   // thread tile: 4 batch rows x 1 hidden unit
   const int j = j0 + jl;
   const float* bh = bhh + d * 3 * H;
@@ -192,140 +213,168 @@ gru_fwd_persistent_kernel(const float* __restrict__ Gx, const float* __restrict_
   const float* wr = sW + (0 * kPJ + jl) * kPLdW;
   const float* wz = sW + (1 * kPJ + jl) * kPLdW;
   const float* wn = sW + (2 * kPJ + jl) * kPLdW;
-  cluster.sync();                                                   // every CTA initialised before remote writes
   for (int s = 0; s < T; ++s) {
     const int tt = d == 0 ? s : T - 1 - s;
-    const float* hbuf = sH + (s & 1) * kPB * H;
-    float* hnext = sH + ((s & 1) ^ 1) * kPB * H;
+    const int tp = d == 0 ? tt - 1 : tt + 1;
+    // this step's input projections: issued now, consumed after the recurrent matmul
+    float gxr[4], gxz[4], gxn[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int b = b0 + bl0 + i;
+      gxr[i] = gxz[i] = gxn[i] = 0.f;
+      if (b < B) {
+        const float* gx = Gx + (((long long)b * T + tt) * 2 + d) * 3 * H;
+        gxr[i] = __ldg(gx + j); gxz[i] = __ldg(gx + H + j); gxn[i] = __ldg(gx + 2 * H + j);
+      }
+    }
+    if (s > 0) group_barrier(ctr, (unsigned int)(kPGroup * s));     // h_{t-1} of all 8 CTAs is in L2
+    else __syncthreads();
+    for (int i = tid; i < kPB * (H / 4); i += kPThreads) {
+      const int bl = i / (H / 4), k4 = i % (H / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (s > 0 && b0 + bl < B)
+        v = __ldcg(reinterpret_cast<const float4*>(out + ((long long)(b0 + bl) * T + tp) * 2 * H + d * H + k4 * 4));
+      *reinterpret_cast<float4*>(sH + bl * H + k4 * 4) = v;
+    }
+    __syncthreads();
     float ar[4], az[4], an[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) ar[i] = az[i] = an[i] = 0.f;
-#pragma unroll 2
+#pragma unroll 4
     for (int k = 0; k < H; k += 4) {
       const float4 r4 = *reinterpret_cast<const float4*>(wr + k);
       const float4 z4 = *reinterpret_cast<const float4*>(wz + k);
       const float4 n4 = *reinterpret_cast<const float4*>(wn + k);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float4 h4 = *reinterpret_cast<const float4*>(hbuf + (bl0 + i) * H + k);
+        const float4 h4 = *reinterpret_cast<const float4*>(sH + (bl0 + i) * H + k);
         ar[i] = fmaf(h4.x, r4.x, ar[i]); ar[i] = fmaf(h4.y, r4.y, ar[i]); ar[i] = fmaf(h4.z, r4.z, ar[i]); ar[i] = fmaf(h4.w, r4.w, ar[i]);
         az[i] = fmaf(h4.x, z4.x, az[i]); az[i] = fmaf(h4.y, z4.y, az[i]); az[i] = fmaf(h4.z, z4.z, az[i]); az[i] = fmaf(h4.w, z4.w, az[i]);
         an[i] = fmaf(h4.x, n4.x, an[i]); an[i] = fmaf(h4.y, n4.y, an[i]); an[i] = fmaf(h4.z, n4.z, an[i]); an[i] = fmaf(h4.w, n4.w, an[i]);
       }
     }
-    float hn[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int b = b0 + bl0 + i;
-      hn[i] = 0.f;
       if (b < B) {
-        const float* gx = Gx + (((long long)b * T + tt) * 2 + d) * 3 * H;
         const float ghn = an[i] + bh_n;
-        const float r = sigm(gx[j] + ar[i] + bh_r);
-        const float z = sigm(gx[H + j] + az[i] + bh_z);
-        const float n = tanhf(gx[2 * H + j] + r * ghn);
-        const float hp = hbuf[(bl0 + i) * H + j];
-        hn[i] = (1.f - z) * n + z * hp;
-        out[((long long)b * T + tt) * 2 * H + d * H + j] = hn[i];
+        const float r = sigm(gxr[i] + ar[i] + bh_r);
+        const float z = sigm(gxz[i] + az[i] + bh_z);
+        const float n = tanhf(gxn[i] + r * ghn);
+        const float hp = sH[(bl0 + i) * H + j];
+        out[((long long)b * T + tt) * 2 * H + d * H + j] = (1.f - z) * n + z * hp;
         float* gs = gates + (((long long)b * T + tt) * 2 + d) * 4 * H;
         gs[j] = r; gs[H + j] = z; gs[2 * H + j] = n; gs[3 * H + j] = ghn;
       }
     }
-#pragma unroll
-    for (int rk = 0; rk < kPCluster; ++rk) {
-      float* peer = cluster.map_shared_rank(hnext, rk);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) peer[(bl0 + i) * H + j] = hn[i];
-    }
-    cluster.sync();                                                 // h_t complete everywhere; h_{t-1} buffer reusable
+    // (the next iteration's barrier orders these stores before any other CTA's read, and its leading
+    //  __syncthreads orders this step's sH reads before the refill)
   }
 }
 
-// BPTT in one launch, same cluster shape.  CTA r keeps columns [32r, 32r+32) of W_hh (bf16, 768 x 32) in
-// shared memory.  Per step every CTA rebuilds the gate gradients dgh (32 rows x 768) from the saved gates and
-// the carried dh (redundantly x8, it is elementwise work), then computes its 32 columns of
-// dh_prev = dgh . W_hh + dh * z and pushes them to all 8 CTAs.
-__global__ void __cluster_dims__(kPCluster, 1, 1) __launch_bounds__(kPThreads, 1)
+// BPTT in one cooperative launch, same grouping.  CTA r owns hidden units / W_hh columns [32r, 32r+32): it
+// turns dh of its own units into the gate gradients (which it stores to dGx / dGh -- needed by the
+// weight-gradient GEMMs anyway), meets the group, reads the group's full dGh rows back from L2, and computes
+// its own 32 columns of dh_prev = dGh . W_hh + dh * z, which never leave its registers.
+__global__ void __launch_bounds__(kPThreads, 1)
 gru_bwd_persistent_kernel(const float* __restrict__ dout, const float* __restrict__ out, const float* __restrict__ gates,
-                          const float* __restrict__ Whh, float* __restrict__ dGx, float* __restrict__ dGh,
-                          float* __restrict__ Hprev, int B, int T) {
+                          const float* __restrict__ Whh, float* __restrict__ dGx, float* dGh,
+                          float* __restrict__ Hprev, GruPersist q) {
   extern __shared__ __align__(16) float smem[];
   constexpr int H = kPH;
-  float* sD = smem;                                     // [kPB][3H] dgh
-  float* sCarry = sD + kPB * 3 * H;                     // [2][kPB][H] dh carried from the later step
-  float* sC = sCarry + 2 * kPB * H;                     // [kPB][kPJ] dh*z for this CTA's columns
-  __nv_bfloat16* sW = reinterpret_cast<__nv_bfloat16*>(sC + kPB * kPJ);   // [3H][kPJ]
-  cg::cluster_group cluster = cg::this_cluster();
-  const int k0 = blockIdx.x * kPJ, b0 = blockIdx.y * kPB, d = blockIdx.z;
+  const int B = q.B, T = q.T;
+  float* sD = smem;                                     // [kPB][3H]  dGh rows of the group
+  float* sW = sD + kPB * 3 * H;                         // [3H][kPJ]  W_hh[:, k0:k0+32]
+  const int k0 = blockIdx.x * kPJ, b0 = q.b_base + blockIdx.y * kPB, d = blockIdx.z;
+  unsigned int* ctr = q.sync_ctr + (blockIdx.y * 2 + d);
   const int tid = threadIdx.x;
   const float* W = Whh + (long long)d * 3 * H * H;
-  for (int i = tid; i < 3 * H * kPJ; i += kPThreads) {
-    const int row = i / kPJ, c = i % kPJ;
-    sW[i] = __float2bfloat16_rn(W[(long long)row * H + k0 + c]);
+  for (int i = tid; i < 3 * H * (kPJ / 4); i += kPThreads) {
+    const int row = i / (kPJ / 4), c4 = i % (kPJ / 4);
+    *reinterpret_cast<float4*>(sW + row * kPJ + c4 * 4) =
+        *reinterpret_cast<const float4*>(W + (long long)row * H + k0 + c4 * 4);
   }
-  for (int i = tid; i < kPB * H; i += kPThreads) sCarry[i] = 0.f;
-  const int kl = tid & 31, bl0 = (tid >> 5) * 4;
-  cluster.sync();
+  const int kl = tid & 31, bl0 = (tid >> 5) * 4;        // thread tile: 4 batch rows x 1 hidden unit (j = k0 + kl)
+  const int j = k0 + kl;
+  float carry[4] = {0.f, 0.f, 0.f, 0.f};                // dh flowing back from the later time step
   for (int bs = 0; bs < T; ++bs) {
     const int tt = d == 0 ? T - 1 - bs : bs;
     const int tp = d == 0 ? tt - 1 : tt + 1;
     const bool has_prev = tp >= 0 && tp < T;
-    const float* cin = sCarry + (bs & 1) * kPB * H;
-    float* cnext = sCarry + ((bs & 1) ^ 1) * kPB * H;
-    for (int i = tid; i < kPB * H; i += kPThreads) {
-      const int bl = i / H, j = i % H;
-      const int b = b0 + bl;
-      float dr_pre = 0.f, dz_pre = 0.f, dn_pre = 0.f, r = 0.f, dhz = 0.f;
+    float dhz[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int b = b0 + bl0 + i;
+      dhz[i] = 0.f;
       if (b < B) {
         const long long bt = (long long)b * T + tt;
         const float* gs = gates + (bt * 2 + d) * 4 * H;
-        r = gs[j];
-        const float z = gs[H + j], n = gs[2 * H + j], ghn = gs[3 * H + j];
-        const float hp = has_prev ? out[((long long)b * T + tp) * 2 * H + d * H + j] : 0.f;
-        const float dh = dout[bt * 2 * H + d * H + j] + cin[bl * H + j];
-        dn_pre = dh * (1.f - z) * (1.f - n * n);
-        dz_pre = dh * (hp - n) * z * (1.f - z);
-        dr_pre = dn_pre * ghn * r * (1.f - r);
-        dhz = dh * z;
-        if ((j >> 5) == (int)blockIdx.x) {                // each CTA stores its own 32-unit slice
-          float* gx = dGx + (bt * 2 + d) * 3 * H;
-          float* gh = dGh + (bt * 2 + d) * 3 * H;
-          gx[j] = dr_pre; gx[H + j] = dz_pre; gx[2 * H + j] = dn_pre;
-          gh[j] = dr_pre; gh[H + j] = dz_pre; gh[2 * H + j] = dn_pre * r;
-          Hprev[(bt * 2 + d) * H + j] = hp;
-        }
+        const float r = __ldg(gs + j), z = __ldg(gs + H + j), n = __ldg(gs + 2 * H + j), ghn = __ldg(gs + 3 * H + j);
+        const float hp = has_prev ? __ldg(out + ((long long)b * T + tp) * 2 * H + d * H + j) : 0.f;
+        const float dh = __ldg(dout + bt * 2 * H + d * H + j) + carry[i];
+        const float dn_pre = dh * (1.f - z) * (1.f - n * n);
+        const float dz_pre = dh * (hp - n) * z * (1.f - z);
+        const float dr_pre = dn_pre * ghn * r * (1.f - r);
+        dhz[i] = dh * z;
+        float* gx = dGx + (bt * 2 + d) * 3 * H;
+        float* gh = dGh + (bt * 2 + d) * 3 * H;
+        gx[j] = dr_pre; gx[H + j] = dz_pre; gx[2 * H + j] = dn_pre;
+        gh[j] = dr_pre; gh[H + j] = dz_pre; gh[2 * H + j] = dn_pre * r;
+        Hprev[(bt * 2 + d) * H + j] = hp;
       }
-      sD[bl * 3 * H + j] = dr_pre;
-      sD[bl * 3 * H + H + j] = dz_pre;
-      sD[bl * 3 * H + 2 * H + j] = dn_pre * r;
-      if ((j >> 5) == (int)blockIdx.x) sC[bl * kPJ + (j & 31)] = dhz;
+    }
+    if (bs == T - 1) break;                              // dh of the step before the first is not needed
+    group_barrier(ctr, (unsigned int)(kPGroup * (bs + 1)));   // every CTA's dGh slice of this step is in L2
+    for (int i = tid; i < kPB * (3 * H / 4); i += kPThreads) {
+      const int bl = i / (3 * H / 4), c4 = i % (3 * H / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (b0 + bl < B)
+        v = __ldcg(reinterpret_cast<const float4*>(dGh + (((long long)(b0 + bl) * T + tt) * 2 + d) * 3 * H + c4 * 4));
+      *reinterpret_cast<float4*>(sD + bl * 3 * H + c4 * 4) = v;
     }
     __syncthreads();
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
     for (int row = 0; row < 3 * H; row += 4) {
-      float wv[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) wv[q] = __bfloat162float(sW[(row + q) * kPJ + kl]);
+      const float w0 = sW[(row + 0) * kPJ + kl], w1 = sW[(row + 1) * kPJ + kl];
+      const float w2 = sW[(row + 2) * kPJ + kl], w3 = sW[(row + 3) * kPJ + kl];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float4 d4 = *reinterpret_cast<const float4*>(sD + (bl0 + i) * 3 * H + row);
-        acc[i] = fmaf(d4.x, wv[0], acc[i]);
-        acc[i] = fmaf(d4.y, wv[1], acc[i]);
-        acc[i] = fmaf(d4.z, wv[2], acc[i]);
-        acc[i] = fmaf(d4.w, wv[3], acc[i]);
+        acc[i] = fmaf(d4.x, w0, acc[i]);
+        acc[i] = fmaf(d4.y, w1, acc[i]);
+        acc[i] = fmaf(d4.z, w2, acc[i]);
+        acc[i] = fmaf(d4.w, w3, acc[i]);
       }
     }
-    float v[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = acc[i] + sC[(bl0 + i) * kPJ + kl];
-#pragma unroll
-    for (int rk = 0; rk < kPCluster; ++rk) {
-      float* peer = cluster.map_shared_rank(cnext, rk);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) peer[(bl0 + i) * H + k0 + kl] = v[i];
-    }
-    cluster.sync();      // carry complete everywhere; also orders this step's sD/sC reads before the next writes
+    for (int i = 0; i < 4; ++i) carry[i] = acc[i] + dhz[i];
+    // (the next barrier's leading __syncthreads orders these sD reads before the refill)
   }
+}
+
+// Cooperative launches (co-residency of a group is what makes the barrier deadlock-free) over chunks of
+// batch tiles that fit the device at one CTA per SM.
+template <typename F>
+int launch_gru_persistent(const void* kern, const char* name, size_t smem, int B, int T, unsigned int* sync_ws,
+                          cudaStream_t stream, F fill_args) {
+  SED_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  SED_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPThreads, smem));
+  const int max_tiles = per_sm * sm_count() / (kPGroup * 2);
+  SED_REQUIRE(max_tiles >= 1, "%s: the device cannot hold one batch tile", name);
+  const int tiles = (B + kPB - 1) / kPB;
+  SED_CUDA(cudaMemsetAsync(sync_ws, 0, sizeof(unsigned int) * 2 * (size_t)tiles, stream));
+  for (int t0 = 0; t0 < tiles; t0 += max_tiles) {
+    const int nt = tiles - t0 < max_tiles ? tiles - t0 : max_tiles;
+    GruPersist q{sync_ws + 2 * t0, B, T, t0 * kPB};
+    void* args[12];
+    const int n = fill_args(args);
+    args[n] = &q;
+    SED_CUDA(cudaLaunchCooperativeKernel(kern, dim3(kPGroup, nt, 2), dim3(kPThreads), args, smem, stream));
+    count_launch();
+  }
+  return 0;
 }
 
 // (R, K) fp32 -> (R, 3K) bf16:  which = 0: [hi | lo | hi]   (left operand)
@@ -380,18 +429,18 @@ using namespace sed;
 
 extern "C" {
 
-int sed_gru_fwd(const float* gx, const float* w_hh, const float* b_hh, float* out, float* gates, int B, int T,
-                int H, sed_stream_t stream) {
+int sed_gru_fwd(const float* gx, const float* w_hh, const float* b_hh, float* out, float* gates, void* sync_ws,
+                int B, int T, int H, sed_stream_t stream) {
   SED_REQUIRE(gx && w_hh && b_hh && out && gates, "sed_gru_fwd: null pointer");
   SED_REQUIRE(H % kHT == 0 && H % 4 == 0 && H <= 512, "sed_gru_fwd: hidden size %d unsupported", H);
   if (B == 0 || T == 0) return 0;
-  if (H == kPH) {
-    const size_t psmem = sizeof(float) * (size_t)(3 * kPJ * kPLdW + 2 * kPB * kPH);
-    SED_CUDA(cudaFuncSetAttribute(gru_fwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-    const dim3 pgrid(kPCluster, (B + kPB - 1) / kPB, 2);
-    gru_fwd_persistent_kernel<<<pgrid, kPThreads, psmem, (cudaStream_t)stream>>>(gx, w_hh, b_hh, out, gates, B, T);
-    SED_LAUNCH_CHECK("gru_fwd_persistent_kernel");
-    return 0;
+  if (H == kPH && sync_ws != nullptr) {
+    const size_t psmem = sizeof(float) * (size_t)(3 * kPJ * kPLdW + kPB * kPH);
+    return launch_gru_persistent((const void*)gru_fwd_persistent_kernel, "sed_gru_fwd", psmem, B, T,
+                                 reinterpret_cast<unsigned int*>(sync_ws), (cudaStream_t)stream, [&](void** a) {
+                                   a[0] = (void*)&gx; a[1] = (void*)&w_hh; a[2] = (void*)&b_hh; a[3] = (void*)&out; a[4] = (void*)&gates;
+                                   return 5;
+                                 });
   }
   const size_t smem = sizeof(float) * (size_t)(3 * kHT * (H + 4) + kBT * H);
   SED_CUDA(cudaFuncSetAttribute(gru_fwd_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -409,12 +458,14 @@ int sed_gru_bwd(const float* dout, const float* out, const float* gates, const f
   SED_REQUIRE(H % kHT == 0 && H % 4 == 0 && H <= 256, "sed_gru_bwd: hidden size %d unsupported", H);
   if (B == 0 || T == 0) return 0;
   if (H == kPH) {
-    const size_t psmem = sizeof(float) * (size_t)(kPB * 3 * kPH + 2 * kPB * kPH + kPB * kPJ) + 2 * (size_t)(3 * kPH * kPJ);
-    SED_CUDA(cudaFuncSetAttribute(gru_bwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-    const dim3 pgrid(kPCluster, (B + kPB - 1) / kPB, 2);
-    gru_bwd_persistent_kernel<<<pgrid, kPThreads, psmem, (cudaStream_t)stream>>>(dout, out, gates, w_hh, dgx, dgh, hprev, B, T);
-    SED_LAUNCH_CHECK("gru_bwd_persistent_kernel");
-    return 0;
+    // the carry scratch is not needed (dh never leaves registers); its head holds the group counters
+    const size_t psmem = sizeof(float) * (size_t)(kPB * 3 * kPH + 3 * kPH * kPJ);
+    return launch_gru_persistent((const void*)gru_bwd_persistent_kernel, "sed_gru_bwd", psmem, B, T,
+                                 reinterpret_cast<unsigned int*>(carry), (cudaStream_t)stream, [&](void** a) {
+                                   a[0] = (void*)&dout; a[1] = (void*)&out; a[2] = (void*)&gates; a[3] = (void*)&w_hh;
+                                   a[4] = (void*)&dgx; a[5] = (void*)&dgh; a[6] = (void*)&hprev;
+                                   return 7;
+                                 });
   }
   const size_t smem = sizeof(float) * (size_t)(3 * H * kHT + kBT * 3 * H + kBT * kHT);
   SED_CUDA(cudaFuncSetAttribute(gru_bwd_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

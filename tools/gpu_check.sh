@@ -29,6 +29,13 @@ for w in $WHAT; do
     kbench)
       timeout 600 python tools/bench_kernels.py --batch 64 > gpurun_out/kbench.log 2>&1
       echo "kbench exit $?" | tee -a gpurun_out/summary.txt; tail -40 gpurun_out/kbench.log;;
+    umma_shift)
+      timeout 120 tools/experiments/umma_shift_test > gpurun_out/umma_shift.log 2>&1
+      echo "umma_shift exit $?" | tee -a gpurun_out/summary.txt; cat gpurun_out/umma_shift.log;;
+    ncu_gru)
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:gru_.*persistent -s 4 -c 2 \
+          -f -o gpurun_out/gru_prof python tools/prof_gru.py > gpurun_out/ncu_gru.log 2>&1
+      echo "ncu_gru exit $?" | tee -a gpurun_out/summary.txt; tail -3 gpurun_out/ncu_gru.log;;
     kbench256)
       timeout 600 python tools/bench_kernels.py --batch 256 --what conv > gpurun_out/kbench256.log 2>&1
       echo "kbench256 exit $?" | tee -a gpurun_out/summary.txt; tail -40 gpurun_out/kbench256.log;;
