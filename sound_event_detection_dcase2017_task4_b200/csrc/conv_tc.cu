@@ -15,7 +15,9 @@
 // * both land in 128B-swizzled K-major shared-memory tiles that tcgen05.mma consumes directly;
 //   fp32 accumulators live in TMEM (double buffered: the epilogue of tile i overlaps the MMAs
 //   of tile i+1).
-// * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2-5 = epilogue:
+// * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2-9 = epilogue
+//   (two warps per TMEM lane quarter, each taking every other 32-column chunk -- the K = 576 layers
+//   are epilogue-bound with one warp per quarter):
 //   tcgen05.ld -> bf16 NHWC store, and per-channel sum / sum-of-squares of the fp32
 //   accumulators for the training-mode BatchNorm that follows (warp-transpose reduction,
 //   accumulated per CTA in shared memory, flushed once: deterministic two-level reduction).
@@ -31,8 +33,8 @@ using namespace tc;
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                       // bf16 elements = one 128 B swizzle row
 constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
-constexpr int kNumThreads = 192;                  // 6 warps
-constexpr int kEpiThreads = 128;
+constexpr int kNumThreads = 320;                  // 10 warps: TMA, MMA, 8 epilogue
+constexpr int kEpiThreads = 256;                  // two warps per TMEM lane quarter, interleaved over 32-column chunks
 
 template <int kN> struct Cfg {
   static constexpr int kBBytes = kN * kBlockK * 2;
@@ -160,8 +162,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;              // which of the two warps of this quarter
     const int row = q * 32 + lane;
     const int r_h = row / p.W, r_w = row % p.W;
     int it = 0;
@@ -180,7 +183,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const bool ok = m < p.gemm_m;
         float* drow = p.out_f32 + m * p.Cout + n_tile * kN;
 #pragma unroll 1
-        for (int c = 0; c < kN / 32; ++c) {
+        for (int c = half; c < kN / 32; c += 2) {
           float v[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kN + c * 32, v);
           if (ok) {
@@ -199,7 +202,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
       __nv_bfloat16* dst = p.y + (((long long)b * p.H + h) * p.W + r_w) * p.Cout + n_tile * kN;
 #pragma unroll 1
-      for (int c = 0; c < kN / 32; ++c) {
+      for (int c = half; c < kN / 32; c += 2) {
         float v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kN + c * 32, v);
         if (valid) {

@@ -165,6 +165,217 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __gri
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Weight gradient, "kw-group" tiling (the kernel the 3x3 layers use).
+//
+//   dW[kh][kw][co][ci] = sum_{b,h,w'} dY[b][h][w' - (kw-1)][co] * X[b][h + kh - 1][w'][ci]
+//
+// A CTA owns one kw (or, for Cout = 64, a pair of kw stacked in the M dimension), a 128-row co tile,
+// a kN-column ci tile and a split of the pixel range, and accumulates the THREE kh taps at once:
+//   * the dY tile is loaded with its TMA box start at w0 = -(kw-1): the one-pixel shift and its zero
+//     column come from TMA's out-of-bounds fill, so pixel rows never wrap across image rows;
+//   * ONE X tile with a halo image row above and below serves all three kh: the tap's row shift
+//     (kh * W pixels = kh * W * 128 B, a multiple of 1024 B for W >= 8) is applied to the start address
+//     of the MN-major shared-memory descriptor (128B-swizzle phase is a function of the absolute
+//     address: tools/experiments/umma_shift_test.cu);
+//   * three fp32 accumulators [128 x kN] live side by side in TMEM (384 columns for kN = 128).
+// Per 128-pixel stage this moves 68-80 KB through TMA for 24 MMAs (1536 tensor cycles) instead of 64 KB
+// for 8 MMAs (512 cycles) in the one-tap-per-CTA version: 2.5x less L2->SMEM traffic per FLOP.
+template <int kN> struct KwCfg {
+  static constexpr int kBSlabs = kN / 64;
+  static constexpr uint32_t kTmemCols = (3 * kN <= 256) ? 256 : 512;
+};
+
+struct KwParams {
+  int B, H, W, Cin, Cout;
+  int bh, tiles_h;
+  int m_tiles, n_tiles, splits, kw_groups;
+  int pair;                // Cout == 64: M rows 0..63 = kw_a, rows 64..127 = kw_b
+  int x_rows;              // 128 + 2*W pixel rows in the X halo tile
+  int stage_bytes, stages;
+  int k_total;
+  float* out;              // [splits][9][Cout][Cin]
+  long long slab_stride;
+};
+
+template <int kN>
+__global__ void __launch_bounds__(kThreadsW, 1)
+conv3x3_wgrad_kw_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
+                        const KwParams p) {
+  using C = KwCfg<kN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[4], empty_bar[4], done_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  int rest = blockIdx.x;
+  const int split = rest % p.splits; rest /= p.splits;
+  const int n_tile = rest % p.n_tiles; rest /= p.n_tiles;
+  const int m_tile = rest % p.m_tiles;
+  const int kwg = rest / p.m_tiles;
+  // kw of accumulator rows [0,64) and [64,128)
+  const int kw_a = p.pair ? 2 * kwg : kwg;
+  const int kw_b = p.pair ? (2 * kwg + 1 < 3 ? 2 * kwg + 1 : -1) : kwg;
+  const int per = (p.k_total + p.splits - 1) / p.splits;
+  const int k_begin = split * per;
+  const int k_end = min(p.k_total, k_begin + per);
+  const uint32_t x_slab_bytes = (uint32_t)p.x_rows * 128u;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmap_dy);
+    tma_prefetch_desc(&tmap_x);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<C::kTmemCols>(&tmem_base_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  const int a_slabs = p.pair ? (kw_b >= 0 ? 2 : 1) : (p.Cout >= 128 ? 2 : 1);
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t bytes = (uint32_t)a_slabs * kSlabBytes + (uint32_t)C::kBSlabs * x_slab_bytes;
+      for (int kt = k_begin; kt < k_end; ++kt) {
+        const int b = kt / p.tiles_h;
+        const int h0 = (kt % p.tiles_h) * p.bh;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * p.stage_bytes;
+        uint8_t* sx = sa + 2 * kSlabBytes;
+        mbar_arrive_expect_tx(&full_bar[stage], bytes);
+        if (p.pair) {
+          tma_load_4d(sa, &tmap_dy, &full_bar[stage], 0, -(kw_a - 1), h0, b);
+          if (kw_b >= 0) tma_load_4d(sa + kSlabBytes, &tmap_dy, &full_bar[stage], 0, -(kw_b - 1), h0, b);
+        } else {
+          for (int s = 0; s < a_slabs; ++s)
+            tma_load_4d(sa + s * kSlabBytes, &tmap_dy, &full_bar[stage], m_tile * 128 + s * 64, -(kw_a - 1), h0, b);
+        }
+#pragma unroll
+        for (int s = 0; s < C::kBSlabs; ++s)
+          tma_load_4d(sx + s * x_slab_bytes, &tmap_x, &full_bar[stage], n_tile * kN + s * 64, 0, h0 - 1, b);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, kN, 1, 1);
+      const uint32_t a_lbo = a_slabs == 2 ? kSlabBytes : 0;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kt = k_begin; kt < k_end; ++kt) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * p.stage_bytes);
+        const uint32_t sx = sa + 2 * kSlabBytes;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const uint32_t sxk = sx + (uint32_t)(kh * p.W) * 128u;      // halo tile starts at image row h0 - 1
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {                            // 128 pixels = 8 x K16
+            const uint64_t da = umma_desc_sw128(sa + ks * 2048, a_lbo, 1024);
+            const uint64_t db = umma_desc_sw128(sxk + ks * 2048, x_slab_bytes, 1024);
+            umma_bf16(tmem_base + kh * kN, da, db, idesc, (kt > k_begin || ks > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&done_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;                    // accumulator row
+    int kw, co;
+    bool valid;
+    if (p.pair) {
+      kw = row < 64 ? kw_a : kw_b;
+      co = row & 63;
+      valid = kw >= 0;
+    } else {
+      kw = kw_a;
+      co = m_tile * 128 + row;
+      valid = co < p.Cout;
+    }
+    const bool have = k_end > k_begin;
+    if (have) {
+      mbar_wait(&done_bar, 0);
+      tcgen05_fence_after();
+    }
+#pragma unroll 1
+    for (int kh = 0; kh < 3; ++kh) {
+      const int tap = kh * 3 + (valid ? kw : 0);
+      float* dst = p.out + (long long)split * p.slab_stride + ((long long)tap * p.Cout + (valid ? co : 0)) * p.Cin + n_tile * kN;
+#pragma unroll 1
+      for (int c = 0; c < kN / 32; ++c) {
+        float v[32];
+        if (have) {
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + kh * kN + c * 32, v);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+        if (valid) {
+          float4* d4 = reinterpret_cast<float4*>(dst + c * 32);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) d4[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
+}
+
+struct KwPlan {
+  int kN, kw_groups, m_tiles, n_tiles, splits, stages, stage_bytes, x_rows, pair, bh, tiles_h, k_total;
+};
+
+KwPlan make_kw_plan(int B, int H, int W, int Cin, int Cout) {
+  KwPlan q;
+  q.kN = Cin >= 128 ? 128 : 64;
+  q.pair = Cout == 64 ? 1 : 0;
+  q.kw_groups = q.pair ? 2 : 3;
+  q.m_tiles = q.pair ? 1 : (Cout + 127) / 128;
+  q.n_tiles = Cin / q.kN;
+  q.bh = 128 / W;
+  q.tiles_h = (H + q.bh - 1) / q.bh;
+  q.k_total = B * q.tiles_h;
+  q.x_rows = 128 + 2 * W;
+  q.stage_bytes = 2 * kSlabBytes + (q.kN / 64) * q.x_rows * 128;
+  q.stages = (232448 - 2048) / q.stage_bytes;
+  if (q.stages > 4) q.stages = 4;
+  const int items = q.kw_groups * q.m_tiles * q.n_tiles;
+  long long splits = (2LL * sm_count() + items - 1) / items;      // ~2 CTAs worth of work per SM
+  if (splits > q.k_total) splits = q.k_total;
+  if (splits < 1) splits = 1;
+  q.splits = (int)splits;
+  return q;
+}
+
+template <int kN>
+int launch_wgrad_kw(const CUtensorMap& tdy, const CUtensorMap& tx, const KwParams& p, int grid, cudaStream_t stream) {
+  auto kern = conv3x3_wgrad_kw_kernel<kN>;
+  const int smem = p.stages * p.stage_bytes + 1024;
+  SED_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<grid, kThreadsW, smem, stream>>>(tdy, tx, p);
+  SED_LAUNCH_CHECK("conv3x3_wgrad_kw_kernel");
+  return 0;
+}
+
 template <int kN>
 int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const WgradParams& p, int grid, cudaStream_t stream) {
   auto kern = conv3x3_wgrad_tc_kernel<kN>;
@@ -183,56 +394,46 @@ extern "C" {
 
 // Number of split-K slabs sed_conv3x3_tc_wgrad will write for this shape (workspace sizing).
 int sed_conv3x3_tc_wgrad_splits(int B, int H, int W, int Cin, int Cout) {
-  if (W <= 0 || 128 % W != 0) return 0;
-  const int bh = 128 / W;
-  const int kN = Cin >= 128 ? 128 : 64;
-  const int items = 9 * ((Cout + 127) / 128) * (Cin / kN);
-  const long long k_total = (long long)B * ((H + bh - 1) / bh);
-  long long splits = (2LL * sm_count() + items - 1) / items;      // ~2 CTAs worth of work per SM
-  if (splits > k_total) splits = k_total;
-  if (splits < 1) splits = 1;
-  return (int)splits;
+  if (W < 8 || 128 % W != 0 || Cin < 64 || Cout < 64) return 0;
+  return make_kw_plan(B, H, W, Cin, Cout).splits;
 }
 
 int sed_conv3x3_tc_wgrad(const void* dy, const void* x, float* slabs, int B, int H, int W, int Cin, int Cout,
                          sed_stream_t stream) {
   SED_REQUIRE(dy && x && slabs, "sed_conv3x3_tc_wgrad: null pointer");
   SED_REQUIRE(B > 0 && H > 0, "sed_conv3x3_tc_wgrad: empty batch");
-  SED_REQUIRE(W >= 8 && W <= 128 && 128 % W == 0, "sed_conv3x3_tc_wgrad: W=%d must divide 128 and be >= 8", W);
+  SED_REQUIRE(W >= 8 && W <= 64 && 128 % W == 0, "sed_conv3x3_tc_wgrad: W=%d must divide 128 and lie in [8, 64]", W);
   SED_REQUIRE(Cin % 64 == 0 && Cin >= 64 && (Cin == 64 || Cin % 128 == 0), "sed_conv3x3_tc_wgrad: Cin=%d unsupported", Cin);
   SED_REQUIRE(Cout == 64 || Cout % 128 == 0, "sed_conv3x3_tc_wgrad: Cout=%d unsupported", Cout);
   SED_REQUIRE(aligned(slabs, 16), "sed_conv3x3_tc_wgrad: workspace must be 16-byte aligned");
-  const int kN = Cin >= 128 ? 128 : 64;
-  WgradParams p;
+  const KwPlan q = make_kw_plan(B, H, W, Cin, Cout);
+  SED_REQUIRE(q.stages >= 2, "sed_conv3x3_tc_wgrad: stage of %d bytes does not fit twice in shared memory", q.stage_bytes);
+  KwParams p;
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
-  p.bh = 128 / W;
-  p.tiles_h = (H + p.bh - 1) / p.bh;
-  p.m_tiles = (Cout + 127) / 128;
-  p.n_tiles = Cin / kN;
-  p.splits = sed_conv3x3_tc_wgrad_splits(B, H, W, Cin, Cout);
-  p.a_slabs = Cout == 64 ? 1 : 2;
-  p.gemm = 0;
-  p.k_total = B * p.tiles_h;
+  p.bh = q.bh; p.tiles_h = q.tiles_h;
+  p.m_tiles = q.m_tiles; p.n_tiles = q.n_tiles; p.splits = q.splits; p.kw_groups = q.kw_groups;
+  p.pair = q.pair; p.x_rows = q.x_rows; p.stage_bytes = q.stage_bytes; p.stages = q.stages;
+  p.k_total = q.k_total;
   p.out = slabs;
   p.slab_stride = 9LL * Cout * Cin;
-  const int grid = 9 * p.m_tiles * p.n_tiles * p.splits;
+  const int grid = q.kw_groups * q.m_tiles * q.n_tiles * q.splits;
 
   alignas(64) CUtensorMap tdy, tx;
   {
     const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     const uint64_t strides[3] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
-    const uint32_t box[4] = {64, (uint32_t)W, (uint32_t)p.bh, 1};
+    const uint32_t box[4] = {64, (uint32_t)W, (uint32_t)q.bh, 1};
     if (int rc = tc::make_tmap_bf16(&tdy, dy, 4, dims, strides, box, "wgrad dY map")) return rc;
   }
   {
     const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     const uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
-    const uint32_t box[4] = {64, (uint32_t)W, (uint32_t)p.bh, 1};
-    if (int rc = tc::make_tmap_bf16(&tx, x, 4, dims, strides, box, "wgrad X map")) return rc;
+    const uint32_t box[4] = {64, (uint32_t)W, (uint32_t)(q.bh + 2), 1};
+    if (int rc = tc::make_tmap_bf16(&tx, x, 4, dims, strides, box, "wgrad X halo map")) return rc;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  if (kN == 128) return launch_wgrad<128>(tdy, tx, p, grid, s);
-  return launch_wgrad<64>(tdy, tx, p, grid, s);
+  if (q.kN == 128) return launch_wgrad_kw<128>(tdy, tx, p, grid, s);
+  return launch_wgrad_kw<64>(tdy, tx, p, grid, s);
 }
 
 
