@@ -119,3 +119,37 @@ def test_cpu_tensor_is_rejected():
     bank = pfe.MelBankCSR(torch.from_numpy(pfe.mel_weight_matrix(32000, 1024, 64, 50, 14000)))
     with pytest.raises(RuntimeError, match='CUDA'):
         pfe.logmel(torch.zeros(1, 6400), 320, bank)
+
+
+def test_launcher_resolves_reference_imports_to_the_dropin():
+    """launch.prepare() orders sys.path the way pytorch/main.py:3,18-27 needs so that its bare-name
+    imports bind to the B200 implementations and everything else stays the reference's own file."""
+    ref = '/root/reference'
+    if not os.path.isdir(os.path.join(ref, 'pytorch')):
+        pytest.skip('reference checkout not present (GPU box)')
+    import subprocess
+    import sys
+    code = (
+        "import sys, os\n"
+        "sys.path.insert(0, %r)\n"
+        "from sound_event_detection_dcase2017_task4_b200 import launch\n"
+        "script = launch.prepare(%r)\n"
+        "assert script.endswith('pytorch/main.py') and sys.path[0] == launch.DROPIN_DIR\n"
+        "import models, losses, pytorch_utils, config\n"
+        "from torchlibrosa.stft import Spectrogram, LogmelFilterBank\n"
+        "from torchlibrosa.augmentation import SpecAugmentation\n"
+        "for m in (models, losses, pytorch_utils, sys.modules['torchlibrosa']):\n"
+        "    assert m.__file__.startswith(launch.DROPIN_DIR), m.__file__\n"
+        "assert config.__file__.startswith(%r)\n"
+        "names = ['Cnn_9layers_FrameMax', 'Cnn_9layers_FrameAvg', 'Cnn_9layers_FrameAtt', 'Cnn_9layers_Gru_FrameAvg',\n"
+        "         'Cnn_9layers_Gru_FrameAtt', 'Cnn_9layers_Transformer_FrameAvg', 'Cnn_9layers_Transformer_FrameAtt',\n"
+        "         'ConvBlock', 'AttBlock', 'MultiHead', 'init_layer', 'init_bn', 'init_gru', 'interpolate']\n"
+        "assert all(hasattr(models, n) for n in names)\n"
+        "assert callable(losses.get_loss_func('clip_bce')) and callable(pytorch_utils.do_mixup)\n"
+        "Model = eval('models.' + 'Cnn_9layers_FrameAvg')\n"
+        "m = Model(config.sample_rate, config.window_size, config.hop_size, config.mel_bins, config.fmin, config.fmax,\n"
+        "          config.classes_num)\n"
+        "assert 'spectrogram_extractor.stft.conv_real.weight' in m.state_dict()\n"
+        "print('ok')\n" % (ROOT, ref, ref))
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith('ok'), r.stderr[-2000:]
