@@ -76,7 +76,7 @@ int sed_mel_db_f32(const float* power, long long rows, int n_bins,
 int sed_conv_pack_weights(const float* w_oihw, int Cout, int Cin, void* fwd_pack, void* dgrad_pack,
                           sed_stream_t stream);
 /* grid size the conv kernel will use = number of rows of the stats_partial workspace. */
-int sed_conv3x3_tc_grid(int B, int H, int W, int Cout);
+int sed_conv3x3_tc_grid(int B, int H, int W, int Cin, int Cout);
 /* y = conv3x3(x, w) (bf16 out, fp32 accumulate).  stats_partial (optional):
  * [sed_conv3x3_tc_grid()][2][Cout] per-CTA (sum, sum of squares) of the fp32 results, for the
  * training-mode BatchNorm that follows.  The data gradient is the same call with

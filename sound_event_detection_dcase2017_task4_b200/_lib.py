@@ -26,7 +26,7 @@ SIGNATURES = {
     'sed_stft_power_f32': [P, I, I, I, P, P],
     'sed_mel_db_f32': [P, L, I, P, P, P, I, F, F, I, P, P],
     'sed_conv_pack_weights': [P, I, I, P, P, P],
-    'sed_conv3x3_tc_grid': [I, I, I, I],
+    'sed_conv3x3_tc_grid': [I, I, I, I, I],
     'sed_conv3x3_tc_fwd': [P, P, P, P, I, I, I, I, I, P],
     'sed_conv3x3_tc_wgrad_splits': [I, I, I, I, I],
     'sed_conv3x3_tc_wgrad': [P, P, P, I, I, I, I, I, P],

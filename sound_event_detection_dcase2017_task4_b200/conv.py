@@ -33,7 +33,7 @@ def conv3x3(x, wpack, cout, want_stats=False):
     stats = None
     with torch.cuda.device(x.device):
         if want_stats:
-            grid = _lib.lib().sed_conv3x3_tc_grid(b, h, w, cout)
+            grid = _lib.lib().sed_conv3x3_tc_grid(b, h, w, cin, cout)
             stats = torch.empty((grid, 2, cout), dtype=torch.float32, device=x.device)
         _lib.call('sed_conv3x3_tc_fwd', x.data_ptr(), wpack.data_ptr(), y.data_ptr(), _lib.ptr(stats),
                   b, h, w, cin, cout, _lib.stream_of(x))

@@ -48,14 +48,12 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int P, int
                                    long long* num_batches_tracked, float* __restrict__ scale,
                                    float* __restrict__ shift, float* __restrict__ save_mean,
                                    float* __restrict__ save_invstd) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s, ss;
+  colsum2_block(partial, partial + C, P, 2LL * C, c, c < C, s, ss);
+  if (threadIdx.y != 0) return;
   if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
   if (c >= C) return;
-  double s = 0.0, ss = 0.0;
-  for (int p = 0; p < P; ++p) {
-    s += (double)partial[(long long)p * 2 * C + c];
-    ss += (double)partial[(long long)p * 2 * C + C + c];
-  }
   const double mean = s / count;
   double var = ss / count - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -184,13 +182,10 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int P,
                                        const float* __restrict__ gamma, const float* __restrict__ invstd,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
                                        float* __restrict__ coef /* [3][C]: gamma*invstd, mean(g), mean(g*xhat) */) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, sx = 0.0;
-  for (int p = 0; p < P; ++p) {
-    s += (double)partial[(long long)p * 2 * C + c];
-    sx += (double)partial[(long long)p * 2 * C + C + c];
-  }
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s, sx;
+  colsum2_block(partial, partial + C, P, 2LL * C, c, c < C, s, sx);
+  if (threadIdx.y != 0 || c >= C) return;
   if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)sx : (float)sx;
   if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)s : (float)s;
   if (coef) {
@@ -330,7 +325,7 @@ bn_bwd_reduce_rows_kernel(const __nv_bfloat16* __restrict__ y, const void* __res
     if (ho >= Ho) continue;                          // floor-mode tail row: no gradient
     const __nv_bfloat16* yrow = y + (long long)row * W * C;
     const long long drow = ((long long)b * Ho + ho) * Wo * C;
-#pragma unroll 2
+#pragma unroll 4
     for (int v = threadIdx.x; v < in_vecs; v += kRowThreads) {
       const int w = v >> cv_shift, wo = w / kPool;
       if (wo >= Wo) continue;
@@ -426,6 +421,146 @@ bn_bwd_apply_rows_kernel(const __nv_bfloat16* __restrict__ y, const void* __rest
   }
 }
 
+// ---- 2x2-pool backward, window-structured: a thread-iteration owns one pooled output vector (8 channels) and
+// its 2x2 window of y: ONE dA load + FOUR y loads in flight (instead of 4 x (1 + 1) with the dA vector fetched by
+// four different threads), no integer division, and the floor-mode tail row (odd H) is handled separately.
+template <bool kGradF32>
+__global__ void __launch_bounds__(kRowThreads, 3)
+bn_bwd_reduce_win2_kernel(const __nv_bfloat16* __restrict__ y, const void* __restrict__ dA_,
+                          const float* __restrict__ scale, const float* __restrict__ shift,
+                          const float* __restrict__ mean, const float* __restrict__ invstd, int B, int H, int W,
+                          int C, float* __restrict__ partial) {
+  extern __shared__ float s_red[];                 // [lanes][2*C]
+  const int CV = C >> 3, Ho = H >> 1, Wo = W >> 1;
+  const int cv = threadIdx.x % CV, pl = threadIdx.x / CV, lanes = kRowThreads / CV, cv_shift = __ffs(CV) - 1;
+  float sc[8], sh[8], mu[8], is[8], sg[8], sgx[8];
+  load8f(scale + cv * 8, sc);
+  load8f(shift + cv * 8, sh);
+  load8f(mean + cv * 8, mu);
+  load8f(invstd + cv * 8, is);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sg[k] = sgx[k] = 0.f;
+  const int out_vecs = Wo * CV;
+  const long long in_row = (long long)W * C;
+  const int rows = B * Ho;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int b = row / Ho, ho = row - b * Ho;
+    const __nv_bfloat16* src = y + ((long long)b * H + 2LL * ho) * in_row;
+    const long long drow = (long long)row * Wo * C;
+#pragma unroll 1
+    for (int v = threadIdx.x; v < out_vecs; v += kRowThreads) {
+      const int wo = v >> cv_shift;
+      const long long x0 = ((long long)(2 * wo) * CV + cv) * 8;
+      uint4 raw[4];
+      raw[0] = ldg16(src + x0);
+      raw[1] = ldg16(src + x0 + C);
+      raw[2] = ldg16(src + in_row + x0);
+      raw[3] = ldg16(src + in_row + x0 + C);
+      float g[8];
+      if (kGradF32) load8f(reinterpret_cast<const float*>(dA_) + drow + (long long)v * 8, g);
+      else { const uint4 graw = ldg16(reinterpret_cast<const __nv_bfloat16*>(dA_) + drow + (long long)v * 8); unpack8(graw, g); }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g[k] *= 0.25f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float x[8];
+        unpack8(raw[i], x);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float act = fmaf(x[k], sc[k], sh[k]);
+          const float gk = act > 0.f ? g[k] : 0.f;
+          sg[k] += gk;
+          sgx[k] += gk * (x[k] - mu[k]) * is[k];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    s_red[pl * 2 * C + cv * 8 + k] = sg[k];
+    s_red[pl * 2 * C + C + cv * 8 + k] = sgx[k];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += kRowThreads) {
+    float a = 0.f;
+    for (int l = 0; l < lanes; ++l) a += s_red[l * 2 * C + i];
+    partial[(long long)blockIdx.x * 2 * C + i] = a;
+  }
+}
+
+template <bool kGradF32>
+__global__ void __launch_bounds__(kRowThreads, 3)
+bn_bwd_apply_win2_kernel(const __nv_bfloat16* __restrict__ y, const void* __restrict__ dA_,
+                         const float* __restrict__ scale, const float* __restrict__ shift,
+                         const float* __restrict__ mean, const float* __restrict__ invstd,
+                         const float* __restrict__ coef, int B, int H, int W, int C,
+                         __nv_bfloat16* __restrict__ dy) {
+  const int CV = C >> 3, Ho = H >> 1, Wo = W >> 1;
+  const int cv = threadIdx.x % CV, cv_shift = __ffs(CV) - 1;
+  float sc[8], sh[8], cA[8], cB[8], cC[8];
+  {
+    float mu[8], is[8], c1[8], c2[8], c3[8];
+    load8f(scale + cv * 8, sc);
+    load8f(shift + cv * 8, sh);
+    load8f(mean + cv * 8, mu);
+    load8f(invstd + cv * 8, is);
+    load8f(coef + cv * 8, c1);
+    load8f(coef + C + cv * 8, c2);
+    load8f(coef + 2 * C + cv * 8, c3);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      cA[k] = c1[k] * 0.25f;
+      cB[k] = -c1[k] * c3[k] * is[k];
+      cC[k] = -c1[k] * c2[k] - cB[k] * mu[k];
+    }
+  }
+  const int out_vecs = Wo * CV;
+  const long long in_row = (long long)W * C;
+  const int rows = B * Ho;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int b = row / Ho, ho = row - b * Ho;
+    const long long base = ((long long)b * H + 2LL * ho) * in_row;
+    const long long drow = (long long)row * Wo * C;
+#pragma unroll 1
+    for (int v = threadIdx.x; v < out_vecs; v += kRowThreads) {
+      const int wo = v >> cv_shift;
+      const long long x0 = base + ((long long)(2 * wo) * CV + cv) * 8;
+      const long long offs[4] = {x0, x0 + C, x0 + in_row, x0 + in_row + C};
+      uint4 raw[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) raw[i] = ldg16(y + offs[i]);
+      float g[8];
+      if (kGradF32) load8f(reinterpret_cast<const float*>(dA_) + drow + (long long)v * 8, g);
+      else { const uint4 graw = ldg16(reinterpret_cast<const __nv_bfloat16*>(dA_) + drow + (long long)v * 8); unpack8(graw, g); }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float x[8], o[8];
+        unpack8(raw[i], x);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float act = fmaf(x[k], sc[k], sh[k]);
+          const float gk = act > 0.f ? g[k] : 0.f;
+          o[k] = fmaf(cA[k], gk, fmaf(cB[k], x[k], cC[k]));
+        }
+        store8(dy + offs[i], o);
+      }
+    }
+  }
+  if (H & 1) {                                       // floor-mode tail row: no pooled gradient reaches it
+    const int in_vecs = W * CV;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+      const long long base = ((long long)b * H + (H - 1)) * in_row;
+      for (int v = threadIdx.x; v < in_vecs; v += kRowThreads) {
+        float x[8], o[8];
+        unpack8(ldg16(y + base + (long long)v * 8), x);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = fmaf(cB[k], x[k], cC[k]);
+        store8(dy + base + (long long)v * 8, o);
+      }
+    }
+  }
+}
+
 bool rows_path_ok(int H, int W, int C, int ph, int pw) {
   const int CV = C / 8;
   if (C % 8 != 0 || CV < 1 || CV > kRowThreads || kRowThreads % CV != 0) return false;
@@ -457,7 +592,7 @@ int sed_bn_finalize(const float* partial, int P, int C, double count, const floa
                     long long* num_batches_tracked, float* scale, float* shift, float* save_mean,
                     float* save_invstd, sed_stream_t stream) {
   SED_REQUIRE(partial && scale && shift && P >= 1 && C >= 1 && count >= 1.0, "sed_bn_finalize: bad arguments");
-  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(
+  bn_finalize_kernel<<<ceil_div(C, 32), dim3(32, kColLanes), 0, (cudaStream_t)stream>>>(
       partial, P, C, count, gamma, beta, eps, momentum, running_mean, running_var, num_batches_tracked, scale, shift,
       save_mean, save_invstd);
   SED_LAUNCH_CHECK("bn_finalize_kernel");
@@ -517,7 +652,8 @@ int sed_bn_relu_pool_bwd_reduce(const void* y, const void* dA, int grad_is_f32, 
     cudaStream_t st = (cudaStream_t)stream;
 #define SED_RED(P, F) bn_bwd_reduce_rows_kernel<P, F><<<grid, kRowThreads, smem, st>>>(yy, dA, scale, shift, mean, invstd, B, H, W, C, partial)
     if (ph == 1) { if (grad_is_f32) SED_RED(1, true); else SED_RED(1, false); }
-    else { if (grad_is_f32) SED_RED(2, true); else SED_RED(2, false); }
+    else if (grad_is_f32) bn_bwd_reduce_win2_kernel<true><<<grid, kRowThreads, smem, st>>>(yy, dA, scale, shift, mean, invstd, B, H, W, C, partial);
+    else bn_bwd_reduce_win2_kernel<false><<<grid, kRowThreads, smem, st>>>(yy, dA, scale, shift, mean, invstd, B, H, W, C, partial);
 #undef SED_RED
     SED_LAUNCH_CHECK("bn_bwd_reduce_rows_kernel");
     return 0;
@@ -535,7 +671,7 @@ int sed_bn_relu_pool_bwd_reduce(const void* y, const void* dA, int grad_is_f32, 
 int sed_bn_bwd_finalize(const float* partial, int P, int C, double count, const float* gamma, const float* invstd,
                         float* dgamma, float* dbeta, int accumulate, float* coef, sed_stream_t stream) {
   SED_REQUIRE(partial && invstd && P >= 1 && C >= 1, "sed_bn_bwd_finalize: bad arguments");
-  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(partial, P, C, count, gamma, invstd,
+  bn_bwd_finalize_kernel<<<ceil_div(C, 32), dim3(32, kColLanes), 0, (cudaStream_t)stream>>>(partial, P, C, count, gamma, invstd,
                                                                              dgamma, dbeta, accumulate, coef);
   SED_LAUNCH_CHECK("bn_bwd_finalize_kernel");
   return 0;
@@ -556,7 +692,11 @@ int sed_bn_relu_pool_bwd_apply(const void* y, const void* dA, int grad_is_f32, c
     const int g = rows_grid(B * H, 3);
 #define SED_APP(P, F) bn_bwd_apply_rows_kernel<P, F><<<g, kRowThreads, 0, st>>>(yy, dA, scale, shift, mean, invstd, coef, B, H, W, C, dd)
     if (ph == 1) { if (grad_is_f32) SED_APP(1, true); else SED_APP(1, false); }
-    else { if (grad_is_f32) SED_APP(2, true); else SED_APP(2, false); }
+    else {
+      const int g2 = rows_grid(B * (H / 2), 3);
+      if (grad_is_f32) bn_bwd_apply_win2_kernel<true><<<g2, kRowThreads, 0, st>>>(yy, dA, scale, shift, mean, invstd, coef, B, H, W, C, dd);
+      else bn_bwd_apply_win2_kernel<false><<<g2, kRowThreads, 0, st>>>(yy, dA, scale, shift, mean, invstd, coef, B, H, W, C, dd);
+    }
 #undef SED_APP
     SED_LAUNCH_CHECK("bn_bwd_apply_rows_kernel");
     return 0;

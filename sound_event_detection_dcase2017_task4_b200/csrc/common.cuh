@@ -59,6 +59,32 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+// Deterministic second-level reduction used by every "finalize" kernel: block = (32 columns, kColLanes row lanes).
+// Row lane y sums rows y, y + kColLanes, ... of two [P][stride] fp32 partial arrays (a, b) for column `col`
+// in fp64; the lanes are then combined in fixed order.  The totals are valid in the threadIdx.y == 0 threads.
+constexpr int kColLanes = 16;
+__device__ __forceinline__ void colsum2_block(const float* __restrict__ a, const float* __restrict__ b, int P,
+                                              long long stride, long long col, bool ok, double& sa, double& sb) {
+  __shared__ double s_part[2][kColLanes][33];
+  double xa = 0.0, xb = 0.0;
+  if (ok) {
+    for (int p = threadIdx.y; p < P; p += kColLanes) {
+      xa += (double)a[(long long)p * stride + col];
+      if (b) xb += (double)b[(long long)p * stride + col];
+    }
+  }
+  s_part[0][threadIdx.y][threadIdx.x] = xa;
+  s_part[1][threadIdx.y][threadIdx.x] = xb;
+  __syncthreads();
+  sa = 0.0; sb = 0.0;
+  if (threadIdx.y == 0) {
+#pragma unroll
+    for (int l = 0; l < kColLanes; ++l) {
+      sa += s_part[0][l][threadIdx.x];
+      sb += s_part[1][l][threadIdx.x];
+    }
+  }
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);

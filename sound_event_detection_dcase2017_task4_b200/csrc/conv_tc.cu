@@ -276,60 +276,6 @@ using namespace sed;
 
 extern "C" {
 
-int sed_conv3x3_tc_grid(int B, int H, int W, int Cout) {
-  if (W <= 0 || 128 % W != 0) return 0;
-  const int bh = 128 / W;
-  const int kN = Cout >= 256 ? 256 : Cout;
-  if (kN <= 0 || Cout % kN != 0) return 0;
-  const long long tiles = (long long)B * ((H + bh - 1) / bh) * (Cout / kN);
-  return (int)(tiles < sm_count() ? tiles : sm_count());
-}
-
-int sed_conv3x3_tc_fwd(const void* x, const void* wpack, void* y, float* stats_partial, int B, int H, int W,
-                       int Cin, int Cout, sed_stream_t stream) {
-  SED_REQUIRE(x && wpack && y, "sed_conv3x3_tc_fwd: null pointer");
-  SED_REQUIRE(B > 0 && H > 0, "sed_conv3x3_tc_fwd: empty batch");
-  SED_REQUIRE(W >= 8 && W <= 128 && 128 % W == 0, "sed_conv3x3_tc_fwd: W=%d must divide 128 and be >= 8", W);
-  SED_REQUIRE(Cin % 64 == 0 && Cin >= 64, "sed_conv3x3_tc_fwd: Cin=%d must be a multiple of 64", Cin);
-  SED_REQUIRE(Cout == 64 || Cout == 128 || Cout % 256 == 0, "sed_conv3x3_tc_fwd: Cout=%d unsupported", Cout);
-  SED_REQUIRE(Cout <= 512, "sed_conv3x3_tc_fwd: Cout=%d > 512", Cout);
-  SED_REQUIRE(aligned(y, 16), "sed_conv3x3_tc_fwd: output must be 16-byte aligned");
-  const int kN = Cout >= 256 ? 256 : Cout;
-  ConvParams p;
-  p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
-  p.bh = 128 / W;
-  p.tiles_h = (H + p.bh - 1) / p.bh;
-  p.tiles_n = Cout / kN;
-  p.num_tiles = B * p.tiles_h * p.tiles_n;
-  p.kb_per_tap = Cin / 64;
-  p.y = reinterpret_cast<__nv_bfloat16*>(y);
-  p.stats = stats_partial;
-  p.gemm_m = 0; p.gemm_kb = 0; p.out_f32 = nullptr; p.bias = nullptr;
-  const int grid = sed_conv3x3_tc_grid(B, H, W, Cout);
-
-  alignas(64) CUtensorMap ta, tb;
-  {
-    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-    const uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
-    const uint32_t box[4] = {64, (uint32_t)W, (uint32_t)p.bh, 1};
-    if (int rc = tc::make_tmap_bf16(&ta, x, 4, dims, strides, box, "conv activation map")) return rc;
-  }
-  {
-    const uint64_t dims[2] = {(uint64_t)9 * Cin, (uint64_t)Cout};
-    const uint64_t strides[1] = {(uint64_t)9 * Cin * 2};
-    const uint32_t box[2] = {64, (uint32_t)kN};
-    if (int rc = tc::make_tmap_bf16(&tb, wpack, 2, dims, strides, box, "conv weight map")) return rc;
-  }
-  cudaStream_t s = (cudaStream_t)stream;
-  switch (kN) {
-    case 64: return launch_conv<64>(ta, tb, p, grid, s);
-    case 128: return launch_conv<128>(ta, tb, p, grid, s);
-    case 256: return launch_conv<256>(ta, tb, p, grid, s);
-  }
-  SED_REQUIRE(false, "sed_conv3x3_tc_fwd: no kernel for N tile %d", kN);
-}
-
-
 // Plain tensor-core GEMM on the same pipeline: out[M][N] = A[M][K] * Bw[N][K]^T (+ bias), A / Bw bf16
 // K-major, out fp32.  K % 64 == 0, N in {64, 128} or a multiple of 256.  Used for the GRU / attention
 // projections (x @ W^T), optionally with the 3-way bf16 split (see sed_split_bf16x3) for fp32-class accuracy.

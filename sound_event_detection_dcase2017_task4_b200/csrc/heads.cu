@@ -15,87 +15,174 @@ namespace {
 
 constexpr int kMaxK = 32;
 
-// out[r][k] = bias[k] + sum_c x[r][c] * W[k][c]      one warp per row
-__global__ void linear_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W,
-                                        const float* __restrict__ bias, long long R, int C, int K,
-                                        float* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long r = warp; r < R; r += nwarps) {
-    float acc[kMaxK];
+constexpr int kMaxKG = kMaxK / 4;         // K padded to float4 groups
+constexpr int kFwdRows = 64;              // rows per block of the forward kernel
+constexpr int kFwdChunk = 32;             // columns of x staged per step
+
+// out[r][k] = bias[k] + sum_c x[r][c] * W[k][c]
+// block = 128 threads = 64 rows x 2 halves of the K groups.  W^T is staged once per block as [c][Kp]
+// (Kp = K padded to a multiple of 4) so that a thread reads its weights as warp-broadcast float4s; x is
+// staged 64 rows x 32 columns at a time (coalesced 128 B row segments, padded rows: conflict-free).
+__global__ void __launch_bounds__(128)
+linear_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
+                        long long R, int C, int K, float* __restrict__ out) {
+  extern __shared__ float4 s_lin4[];
+  const int KG = (K + 3) >> 2, Kp = KG * 4;
+  float* s_w = reinterpret_cast<float*>(s_lin4);                 // [C][Kp]
+  float* s_x = s_w + (size_t)C * Kp;                             // [64][33]
+  for (int i = threadIdx.x; i < C * Kp; i += blockDim.x) {
+    const int c = i / Kp, k = i % Kp;
+    s_w[i] = k < K ? W[(long long)k * C + c] : 0.f;
+  }
+  const int r_loc = threadIdx.x & 63, kh = threadIdx.x >> 6;     // kh is warp-uniform
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r0 = (long long)blockIdx.x * kFwdRows;
+  float4 acc[(kMaxKG + 1) / 2];
 #pragma unroll
-    for (int k = 0; k < kMaxK; ++k) acc[k] = 0.f;
-    for (int c = lane; c < C; c += 32) {
-      const float xv = x[r * C + c];
-#pragma unroll
-      for (int k = 0; k < kMaxK; ++k)
-        if (k < K) acc[k] = fmaf(xv, __ldg(W + (long long)k * C + c), acc[k]);
+  for (int j = 0; j < (kMaxKG + 1) / 2; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* s_w4 = reinterpret_cast<const float4*>(s_w);
+  for (int c0 = 0; c0 < C; c0 += kFwdChunk) {
+    __syncthreads();
+    for (int rr = warp; rr < kFwdRows; rr += 4) {
+      const long long r = r0 + rr;
+      const int c = c0 + lane;
+      s_x[rr * 33 + lane] = (r < R && c < C) ? x[r * C + c] : 0.f;
     }
+    __syncthreads();
+    const int cn = min(kFwdChunk, C - c0);
+    for (int c = 0; c < cn; ++c) {
+      const float xv = s_x[r_loc * 33 + c];
+      const float4* wrow = s_w4 + (size_t)(c0 + c) * KG;
 #pragma unroll
-    for (int k = 0; k < kMaxK; ++k)
-      if (k < K) {
-        const float v = warp_sum(acc[k]);
-        if (lane == 0) out[r * K + k] = v + (bias ? bias[k] : 0.f);
+      for (int j = 0; j < (kMaxKG + 1) / 2; ++j) {
+        const int g = kh + 2 * j;
+        if (g < KG) {
+          const float4 w = wrow[g];
+          acc[j].x = fmaf(xv, w.x, acc[j].x);
+          acc[j].y = fmaf(xv, w.y, acc[j].y);
+          acc[j].z = fmaf(xv, w.z, acc[j].z);
+          acc[j].w = fmaf(xv, w.w, acc[j].w);
+        }
+      }
+    }
+  }
+  const long long r = r0 + r_loc;
+  if (r < R) {
+#pragma unroll
+    for (int j = 0; j < (kMaxKG + 1) / 2; ++j) {
+      const int g = kh + 2 * j;
+      if (g < KG) {
+        const float v[4] = {acc[j].x, acc[j].y, acc[j].z, acc[j].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k = g * 4 + e;
+          if (k < K) out[r * K + k] = v[e] + (bias ? bias[k] : 0.f);
+        }
+      }
+    }
+  }
+}
+
+// dx[r][c..c+3] = sum_k dout[r][k] * W[k][c..c+3]      thread owns 4 consecutive columns, keeps its K x 4 weights in
+// registers and walks the block's rows; dout rows are staged in shared memory and read as broadcasts.
+template <int kKG>
+__global__ void linear_small_dx_kernel(const float* __restrict__ dout, const float* __restrict__ W, long long R, int C,
+                                       int K, float* __restrict__ dx, int accumulate) {
+  extern __shared__ float4 s_lin4[];
+  float* s_d = reinterpret_cast<float*>(s_lin4);                 // [chunk][Kp]
+  constexpr int Kp = kKG * 4, chunk = 32;
+  const int c = threadIdx.x * 4;
+  const bool ok = c < C;
+  float4 w[Kp];
+#pragma unroll
+  for (int k = 0; k < Kp; ++k) {                 // scalar loads: W may be a 4-byte-aligned view into a flat parameter buffer
+    const float* wk = W + (long long)k * C + c;
+    w[k] = (ok && k < K) ? make_float4(wk[0], wk[1], wk[2], wk[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const long long per = (R + gridDim.x - 1) / gridDim.x;
+  const long long r0 = blockIdx.x * per, r1 = min(R, r0 + per);
+  for (long long rb = r0; rb < r1; rb += chunk) {
+    const int n = (int)min((long long)chunk, r1 - rb);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n * Kp; i += blockDim.x) {
+      const int j = i / Kp, k = i % Kp;
+      s_d[i] = k < K ? dout[(rb + j) * K + k] : 0.f;
+    }
+    __syncthreads();
+    if (ok)
+      for (int j = 0; j < n; ++j) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* d4 = reinterpret_cast<const float4*>(s_d + j * Kp);
+#pragma unroll
+        for (int g = 0; g < kKG; ++g) {
+          const float4 d = d4[g];
+          const float dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            a.x = fmaf(dv[e], w[g * 4 + e].x, a.x);
+            a.y = fmaf(dv[e], w[g * 4 + e].y, a.y);
+            a.z = fmaf(dv[e], w[g * 4 + e].z, a.z);
+            a.w = fmaf(dv[e], w[g * 4 + e].w, a.w);
+          }
+        }
+        float4* o = reinterpret_cast<float4*>(dx + (rb + j) * C + c);
+        if (accumulate) {
+          const float4 p = *o;
+          a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+        }
+        *o = a;
       }
   }
 }
 
-// dx[r][c] = sum_k dout[r][k] * W[k][c]
-__global__ void linear_small_dx_kernel(const float* __restrict__ dout, const float* __restrict__ W, long long R, int C,
-                                       int K, float* __restrict__ dx, int accumulate) {
-  const int lane = threadIdx.x & 31;
-  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long r = warp; r < R; r += nwarps) {
-    float d[kMaxK];
-#pragma unroll
-    for (int k = 0; k < kMaxK; ++k) d[k] = (k < K) ? dout[r * K + k] : 0.f;
-    for (int c = lane; c < C; c += 32) {
-      float a = 0.f;
-#pragma unroll
-      for (int k = 0; k < kMaxK; ++k)
-        if (k < K) a = fmaf(d[k], __ldg(W + (long long)k * C + c), a);
-      dx[r * C + c] = accumulate ? dx[r * C + c] + a : a;
-    }
-  }
-}
-
-// partial[blk][k][c] = sum over the block's rows of dout[r][k] * x[r][c];  partial_b[blk][k] = sum dout[r][k]
+// partial_w[blk][k][c..c+3] = sum over the block's rows of dout[r][k] * x[r][c..c+3];  partial_b[blk][k] = sum dout[r][k]
+template <int kKG>
 __global__ void linear_small_dw_kernel(const float* __restrict__ dout, const float* __restrict__ x, long long R, int C,
                                        int K, float* __restrict__ partial_w, float* __restrict__ partial_b) {
-  extern __shared__ float s_d[];                       // [rows_chunk][K]
-  const int chunk = 32;
+  extern __shared__ float4 s_lin4[];
+  float* s_d = reinterpret_cast<float*>(s_lin4);                 // [chunk][Kp]
+  constexpr int Kp = kKG * 4, chunk = 32;
+  const int c = threadIdx.x * 4;
+  const bool ok = c < C;
+  float4 acc[Kp];
+#pragma unroll
+  for (int k = 0; k < Kp; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float bsum = 0.f;
   const long long per = (R + gridDim.x - 1) / gridDim.x;
   const long long r0 = blockIdx.x * per, r1 = min(R, r0 + per);
-  for (int c0 = 0; c0 < C; c0 += blockDim.x) {
-    const int c = c0 + threadIdx.x;
-    float acc[kMaxK];
-#pragma unroll
-    for (int k = 0; k < kMaxK; ++k) acc[k] = 0.f;
-    for (long long rb = r0; rb < r1; rb += chunk) {
-      const int n = (int)min((long long)chunk, r1 - rb);
-      __syncthreads();
-      for (int i = threadIdx.x; i < n * K; i += blockDim.x) s_d[i] = dout[rb * K + i];
-      __syncthreads();
-      if (c < C)
-        for (int j = 0; j < n; ++j) {
-          const float xv = x[(rb + j) * C + c];
-#pragma unroll
-          for (int k = 0; k < kMaxK; ++k)
-            if (k < K) acc[k] = fmaf(s_d[j * K + k], xv, acc[k]);
-        }
+  for (long long rb = r0; rb < r1; rb += chunk) {
+    const int n = (int)min((long long)chunk, r1 - rb);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n * Kp; i += blockDim.x) {
+      const int j = i / Kp, k = i % Kp;
+      s_d[i] = k < K ? dout[(rb + j) * K + k] : 0.f;
     }
-    if (c < C)
+    __syncthreads();
+    if (threadIdx.x < K)
+      for (int j = 0; j < n; ++j) bsum += s_d[j * Kp + threadIdx.x];
+    if (ok)
+      for (int j = 0; j < n; ++j) {
+        const float4 xv = *reinterpret_cast<const float4*>(x + (rb + j) * C + c);
+        const float4* d4 = reinterpret_cast<const float4*>(s_d + j * Kp);
 #pragma unroll
-      for (int k = 0; k < kMaxK; ++k)
-        if (k < K) partial_w[((long long)blockIdx.x * K + k) * C + c] = acc[k];
+        for (int g = 0; g < kKG; ++g) {
+          const float4 d = d4[g];
+          const float dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            acc[g * 4 + e].x = fmaf(dv[e], xv.x, acc[g * 4 + e].x);
+            acc[g * 4 + e].y = fmaf(dv[e], xv.y, acc[g * 4 + e].y);
+            acc[g * 4 + e].z = fmaf(dv[e], xv.z, acc[g * 4 + e].z);
+            acc[g * 4 + e].w = fmaf(dv[e], xv.w, acc[g * 4 + e].w);
+          }
+        }
+      }
   }
-  if (partial_b && threadIdx.x < K) {
-    float a = 0.f;
-    for (long long r = r0; r < r1; ++r) a += dout[r * K + threadIdx.x];
-    partial_b[(long long)blockIdx.x * K + threadIdx.x] = a;
-  }
+  if (ok)
+#pragma unroll
+    for (int k = 0; k < Kp; ++k)
+      if (k < K) *reinterpret_cast<float4*>(partial_w + ((long long)blockIdx.x * K + k) * C + c) = acc[k];
+  if (partial_b && threadIdx.x < K) partial_b[(long long)blockIdx.x * K + threadIdx.x] = bsum;
 }
 
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
@@ -238,15 +325,19 @@ using namespace sed;
 
 extern "C" {
 
-int sed_linear_partials(void) { return sm_count(); }
+int sed_linear_partials(void) { return sm_count() * 4; }
 
 int sed_linear_small_fwd(const float* x, const float* W, const float* bias, long long R, int C, int K, float* out,
                          sed_stream_t stream) {
   SED_REQUIRE(x && W && out, "sed_linear_small_fwd: null pointer");
   SED_REQUIRE(K >= 1 && K <= kMaxK, "sed_linear_small_fwd: K=%d must be in [1, %d]", K, kMaxK);
+  SED_REQUIRE(C >= 1 && C <= 1024, "sed_linear_small_fwd: C=%d must be in [1, 1024]", C);
   if (R == 0) return 0;
-  const int grid = (int)min((R + 7) / 8, (long long)sm_count() * 8);
-  linear_small_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, W, bias, R, C, K, out);
+  const int Kp = (K + 3) / 4 * 4;
+  const size_t smem = ((size_t)C * Kp + kFwdRows * 33) * sizeof(float);
+  SED_CUDA(cudaFuncSetAttribute(linear_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  linear_small_fwd_kernel<<<(unsigned)((R + kFwdRows - 1) / kFwdRows), 128, smem, (cudaStream_t)stream>>>(
+      x, W, bias, R, C, K, out);
   SED_LAUNCH_CHECK("linear_small_fwd_kernel");
   return 0;
 }
@@ -255,15 +346,26 @@ int sed_linear_small_bwd(const float* dout, const float* x, const float* W, long
                          int dx_accumulate, float* partial_w, float* partial_b, sed_stream_t stream) {
   SED_REQUIRE(dout && x && W, "sed_linear_small_bwd: null pointer");
   SED_REQUIRE(K >= 1 && K <= kMaxK, "sed_linear_small_bwd: K=%d must be in [1, %d]", K, kMaxK);
+  SED_REQUIRE(C % 4 == 0 && C >= 4 && C <= 4096, "sed_linear_small_bwd: C=%d must be a multiple of 4, <= 4096", C);
+  SED_REQUIRE(aligned(x, 16) && (!dx || aligned(dx, 16)) && (!partial_w || aligned(partial_w, 16)),
+              "sed_linear_small_bwd: x, dx and partial_w must be 16-byte aligned");
   if (R == 0) return 0;
+  const int threads = (C / 4 + 31) / 32 * 32;
+  const int grid = (int)min(R, (long long)sed_linear_partials());
+  const int kg = (K + 3) / 4;
+  cudaStream_t st = (cudaStream_t)stream;
   if (dx) {
-    const int grid = (int)min((R + 7) / 8, (long long)sm_count() * 8);
-    linear_small_dx_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dout, W, R, C, K, dx, dx_accumulate);
+#define SED_DX(G) linear_small_dx_kernel<G><<<grid, threads, 32 * (G) * 4 * sizeof(float), st>>>(dout, W, R, C, K, dx, dx_accumulate)
+    if (kg <= 2) SED_DX(2); else if (kg <= 5) SED_DX(5); else SED_DX(8);
+#undef SED_DX
     SED_LAUNCH_CHECK("linear_small_dx_kernel");
   }
   if (partial_w) {
-    linear_small_dw_kernel<<<sed_linear_partials(), 256, 32 * K * sizeof(float), (cudaStream_t)stream>>>(
-        dout, x, R, C, K, partial_w, partial_b);
+    // every one of the sed_linear_partials() partial rows must be written: blocks past R write zeros
+    const int gridw = sed_linear_partials();
+#define SED_DW(G) linear_small_dw_kernel<G><<<gridw, threads, 32 * (G) * 4 * sizeof(float), st>>>(dout, x, R, C, K, partial_w, partial_b)
+    if (kg <= 2) SED_DW(2); else if (kg <= 5) SED_DW(5); else SED_DW(8);
+#undef SED_DW
     SED_LAUNCH_CHECK("linear_small_dw_kernel");
   }
   return 0;

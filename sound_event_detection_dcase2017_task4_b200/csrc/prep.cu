@@ -151,12 +151,12 @@ __global__ void mix_pairs_kernel(const float* __restrict__ x, const float* __res
 // out[i] = sum over P partial rows (fp64 accumulate) -- generic deterministic second-level reduction
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int P, long long n, float* __restrict__ out,
                                        int accumulate, float scale) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    double a = 0.0;
-    for (int p = 0; p < P; ++p) a += (double)partial[(long long)p * n + i];
-    const float v = (float)a * scale;
-    out[i] = accumulate ? out[i] + v : v;
-  }
+  const long long i = blockIdx.x * 32LL + threadIdx.x;
+  double a, unused;
+  colsum2_block(partial, nullptr, P, n, i, i < n, a, unused);
+  if (threadIdx.y != 0 || i >= n) return;
+  const float v = (float)a * scale;
+  out[i] = accumulate ? out[i] + v : v;
 }
 
 }  // namespace
@@ -232,8 +232,8 @@ int sed_mix_pairs_f32(const float* x, const float* lam, int B2, int n, float* ou
 int sed_reduce_partials(const float* partial, int P, long long n, float* out, int accumulate, float scale,
                         sed_stream_t stream) {
   SED_REQUIRE(partial && out && P >= 1 && n >= 1, "sed_reduce_partials: bad arguments");
-  const int grid = (int)min((n + 255) / 256, (long long)sm_count() * 8);
-  reduce_partials_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(partial, P, n, out, accumulate, scale);
+  SED_REQUIRE(n < (1LL << 36), "sed_reduce_partials: n too large");
+  reduce_partials_kernel<<<(unsigned)((n + 31) / 32), dim3(32, kColLanes), 0, (cudaStream_t)stream>>>(partial, P, n, out, accumulate, scale);
   SED_LAUNCH_CHECK("reduce_partials_kernel");
   return 0;
 }

@@ -108,26 +108,73 @@ def trunk_forward(model, wave, lam, training, stripes=None, keep=None):
     return x.view(b, tp, c), ctx
 
 
-def trunk_backward(ctx, dfeat, grad_of):
+_SIDE_STREAMS = {}
+# bench.py's per-kernel timing leg sets this to False so that every kernel is timed alone on one stream
+OVERLAP_WGRAD = True
+
+
+def _side_stream(device):
+    """One auxiliary stream per (device, compute stream) for the weight-gradient kernels."""
+    main = torch.cuda.current_stream(device)
+    key = (device.index, main.cuda_stream)
+    side = _SIDE_STREAMS.get(key)
+    if side is None:
+        side = _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return main, side
+
+
+def trunk_backward(ctx, dfeat, grad_of, overlap_wgrad=None):
     """dfeat (B, T/8, 512) fp32 -> parameter gradients written through ``grad_of(param)``
-    (a callable returning the fp32 tensor to fill, or None to skip that parameter)."""
+    (a callable returning the fp32 tensor to fill, or None to skip that parameter).
+
+    Schedule: the critical chain BN-backward_l -> dgrad_l -> BN-backward_{l-1} ... stays on the current
+    stream; the weight gradient of layer l only needs dY_l and the saved input, so it is enqueued on a side
+    stream behind an event.  The BN-backward kernels are HBM-bound and use no shared memory, the weight-gradient
+    kernels are tensor-pipe-bound and use all of it: co-resident on the same SMs they overlap instead of adding
+    up.  The current stream waits for the side stream before returning (the optimizer reads every gradient)."""
+    if overlap_wgrad is None:
+        overlap_wgrad = OVERLAP_WGRAD
     dA = dfeat.contiguous().view(dfeat.shape[0], dfeat.shape[1], 1, dfeat.shape[2])
+    dev = dA.device
+    main, side = _side_stream(dev) if overlap_wgrad else (None, None)
+    used_side = False
     for lc in reversed(ctx.layers):
         dy = ops.bn_relu_pool_bwd(lc.y, dA, lc.st, lc.bn, lc.ph, lc.pw, grad_of(lc.bn.weight),
                                   grad_of(lc.bn.bias))
         gw = grad_of(lc.conv.weight)
+        if gw is not None:
+            if overlap_wgrad:
+                ready = torch.cuda.Event()
+                ready.record(main)
+                side.wait_event(ready)
+                dy.record_stream(side)
+                lc.x_in.record_stream(side)
+                used_side = True
+            with torch.cuda.stream(side) if overlap_wgrad else _NullCtx():
+                if lc.is_c1:
+                    ops.conv_c1_wgrad(lc.x_in, dy, gw)
+                else:
+                    tcconv.conv3x3_wgrad(dy, lc.x_in, out=gw)
         if lc.is_c1:
-            if gw is not None:
-                ops.conv_c1_wgrad(lc.x_in, dy, gw)
             dA = ops.conv_c1_dgrad(dy, lc.conv.weight)                 # (B, T, M) fp32
         else:
-            if gw is not None:
-                tcconv.conv3x3_wgrad(dy, lc.x_in, out=gw)
             dA = tcconv.conv3x3(dy, lc.wd, lc.conv.weight.shape[1])    # bf16 NHWC
         lc.y = lc.x_in = None
     g0w, g0b = grad_of(ctx.bn0.weight), grad_of(ctx.bn0.bias)
     if g0w is not None or g0b is not None:
         ops.bn0_bwd(dA, ctx.logmel, ctx.st0, ctx.bn0, ctx.t_stripes, ctx.f_stripes, ctx.lam, g0w, g0b)
+    if used_side:
+        done = torch.cuda.Event()
+        done.record(side)
+        main.wait_event(done)
+
+
+class _NullCtx(object):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
 
 
 # ------------------------------------------------------------------ heads

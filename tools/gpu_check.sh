@@ -39,6 +39,13 @@ for w in $WHAT; do
     kbench256)
       timeout 600 python tools/bench_kernels.py --batch 256 --what conv > gpurun_out/kbench256.log 2>&1
       echo "kbench256 exit $?" | tee -a gpurun_out/summary.txt; tail -40 gpurun_out/kbench256.log;;
+    kmem)
+      timeout 600 python tools/bench_kernels.py --batch 256 --what bn,c1,lin > gpurun_out/kmem.log 2>&1
+      echo "kmem exit $?" | tee -a gpurun_out/summary.txt; tail -40 gpurun_out/kmem.log;;
+    ncu_conv)
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv3x3 \
+          -f -o gpurun_out/conv_prof python tools/prof_conv.py 256 > gpurun_out/ncu_conv.log 2>&1
+      echo "ncu_conv exit $?" | tee -a gpurun_out/summary.txt; tail -3 gpurun_out/ncu_conv.log;;
     bench)
       timeout 900 python bench.py > gpurun_out/bench.log 2>&1
       echo "bench exit $?" | tee -a gpurun_out/summary.txt; tail -5 gpurun_out/bench.log;;
