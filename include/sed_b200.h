@@ -209,6 +209,20 @@ int sed_dropout_relu_fwd(const float* x, long long n, float p_drop, unsigned lon
                          float* y, sed_stream_t stream);
 int sed_dropout_relu_bwd(const float* dy, const float* y, long long n, float p_drop, float* dx, sed_stream_t stream);
 
+/* ---- frame-wise probabilities -> sound events (onset, offset frame indices), bit-exact ------------
+ * replaces utils/utilities.py:70-123 (frame_prediction_to_event_prediction) and utils/vad.py:11-134
+ * (activity_detection: double threshold, smoothing, salt removal) -- one thread per (clip, class) series.
+ * frame (N, T, K) fp32, clip (N, K) fp32 or NULL (no audio-tagging gate), per-class parameter arrays of
+ * length K (lo_thres may be NULL: single threshold).  sed_vad_count writes the number of pairs per series
+ * and flags (bit 0: the reference would raise IndexError, vad.py:78); the caller turns counts into
+ * exclusive offsets; sed_vad_fill writes the (bgn, fin) pairs in (n, k, pair) order. */
+int sed_vad_count(const float* frame, const float* clip, int N, int T, int K, const float* at_thres,
+                  const float* hi_thres, const float* lo_thres, const int* n_smooth, const int* n_salt,
+                  int* counts, int* flags, sed_stream_t stream);
+int sed_vad_fill(const float* frame, const float* clip, int N, int T, int K, const float* at_thres,
+                 const float* hi_thres, const float* lo_thres, const int* n_smooth, const int* n_salt,
+                 const long long* offsets, int* pairs, sed_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

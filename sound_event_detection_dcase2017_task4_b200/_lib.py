@@ -70,6 +70,8 @@ SIGNATURES = {
     'sed_attention_bwd': [P, P, P, I, I, I, I, I, I, I, F, F, U, U, P, P, P, P, P, P, P],
     'sed_dropout_relu_fwd': [P, L, F, U, U, P, P],
     'sed_dropout_relu_bwd': [P, P, L, F, P, P],
+    'sed_vad_count': [P, P, I, I, I, P, P, P, P, P, P, P, P],
+    'sed_vad_fill': [P, P, I, I, I, P, P, P, P, P, P, P, P],
     'sed_adam_amsgrad': [P, P, P, P, P, L, F, F, F, F, I, F, P],
 }
 _RESTYPES = {

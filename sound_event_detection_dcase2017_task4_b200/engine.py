@@ -109,8 +109,11 @@ def trunk_forward(model, wave, lam, training, stripes=None, keep=None):
 
 
 _SIDE_STREAMS = {}
-# bench.py's per-kernel timing leg sets this to False so that every kernel is timed alone on one stream
-OVERLAP_WGRAD = True
+# Side-stream schedule for the weight gradients (see trunk_backward).  Measured on B200 (tools/ab_step.py, batch 256):
+# 40.05 ms/step with it vs 39.8 ms without -- the one-wave BatchNorm-backward grids (3 CTAs/SM x 80 registers) leave
+# no register room for a co-resident tensor-core CTA, so the kernels serialise anyway.  Off until the BN kernels are
+# made co-residency friendly.
+OVERLAP_WGRAD = False
 
 
 def _side_stream(device):
