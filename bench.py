@@ -54,6 +54,16 @@ def measured_peaks():
     return {'hbm_gbs': 6650.0, 'bf16_burst': 1590.0, 'bf16_sustained': 1400.0, 'source': 'fallback'}
 
 
+def conv_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the conv kernel (average over the 14 forward /
+    data-gradient launches of a step) from the committed `ncu --set full` capture, or None."""
+    path = os.path.join(ROOT, 'profiles', 'conv_traffic.json')
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f).get('dram_bytes_per_launch_avg')
+
+
 class ClockSampler(object):
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
@@ -283,23 +293,25 @@ def run_ours(args):
     # ---- roofline leg: per-entry-point device times of one more step (CUDA events on the launch stream)
     roof = None
     shares = None
-    if rank == 0:
-        peaks = measured_peaks()
-        agg = {}
-        reps = 3
-        from sound_event_detection_dcase2017_task4_b200 import engine as _engine
-        _overlap_was = _engine.OVERLAP_WGRAD
-        _engine.OVERLAP_WGRAD = False                    # serial schedule: every kernel timed alone on one stream
-        for _ in range(reps):
-            _lib.PROFILE = []
-            step_resident()
-            torch.cuda.synchronize()
+    # every rank runs these steps (the step contains the all-reduce); only rank 0 records the events
+    agg = {}
+    reps = 3
+    from sound_event_detection_dcase2017_task4_b200 import engine as _engine
+    _overlap_was = _engine.OVERLAP_WGRAD
+    _engine.OVERLAP_WGRAD = False                        # serial schedule: every kernel timed alone on one stream
+    for _ in range(reps):
+        _lib.PROFILE = [] if rank == 0 else None
+        step_resident()
+        torch.cuda.synchronize()
+        if rank == 0:
             for name, tag, e0, e1 in _lib.PROFILE:
                 a = agg.setdefault(name, [0, 0.0])
                 a[0] += 1
                 a[1] += e0.elapsed_time(e1)
-            _lib.PROFILE = None
-        _engine.OVERLAP_WGRAD = _overlap_was
+        _lib.PROFILE = None
+    _engine.OVERLAP_WGRAD = _overlap_was
+    if rank == 0:
+        peaks = measured_peaks()
         total_ms = sum(v[1] for v in agg.values()) / reps
         shares = {k: {'launches_per_step': v[0] // reps, 'ms_per_step': round(v[1] / reps, 4),
                       'share': round(v[1] / reps / total_ms, 4)}
@@ -310,12 +322,12 @@ def run_ours(args):
         flops_step = bs * (sum(fl) + sum(fl))           # fwd + dgrad of all 7 tensor-core layers
         n_conv, conv_ms = agg['sed_conv3x3_tc_fwd'][0] / reps, agg['sed_conv3x3_tc_fwd'][1] / reps
         achieved = flops_step / (conv_ms * 1e-3) / 1e12
-        roof = {'kernel': 'conv3x3_tc_kernel (sed_conv3x3_tc_fwd: forward + data-gradient launches)',
+        roof = {'kernel': 'conv3x3_halo_kernel (sed_conv3x3_tc_fwd: forward + data-gradient launches)',
                 'bound': 'tensor', 'achieved': round(achieved, 2), 'peak': peaks['bf16_sustained'],
                 'unit': 'TFLOP/s', 'frac': round(achieved / peaks['bf16_sustained'], 4),
                 'peak_source': peaks['source'] + ' bf16_tflops_sustained (kernel timed inside a long step)',
                 'launches_per_step': n_conv, 'avg_launch_ms': round(conv_ms / n_conv, 4),
-                'flop_per_launch_avg': flops_step / n_conv, 'traffic': None,
+                'flop_per_launch_avg': flops_step / n_conv, 'traffic': conv_traffic(),
                 'share_of_step': round(conv_ms / total_ms, 4),
                 'timing': 'CUDA events around every launch of three more steps on the compute stream'}
 
