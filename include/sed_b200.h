@@ -83,6 +83,14 @@ int sed_conv3x3_tc_grid(int B, int H, int W, int Cin, int Cout);
  * x = dY, wpack = the dgrad pack and Cin/Cout swapped. */
 int sed_conv3x3_tc_fwd(const void* x, const void* wpack, void* y, float* stats_partial, int B, int H,
                        int W, int Cin, int Cout, sed_stream_t stream);
+/* Data gradient fused with the FIRST pass of the BatchNorm+ReLU(+2x2 avg-pool) backward of the layer below
+ * (F.relu_(bn(conv(x))) [+ F.avg_pool2d], pytorch/models.py:102-113): dx (B,H,W,Cout) is that layer's dA; y_below is
+ * its raw conv output (B, Hy, W*pool, Cout) with Hy/pool == H (an odd Hy has a floor-mode tail row), scale/shift
+ * its BatchNorm affine of this step.  partial: [sed_conv3x3_tc_grid()][2][Cout] per-CTA sums of g and g*y,
+ * g = unpool(dx)/pool^2 * [y*scale + shift > 0]; feed them to sed_bn_bwd_finalize with mean_for_gy. */
+int sed_conv3x3_tc_dgrad_bnr(const void* dy, const void* wpack_dgrad, void* dx, int B, int H, int W, int Cin,
+                             int Cout, const void* y_below, int Hy, const float* scale_below,
+                             const float* shift_below, int pool, float* partial, sed_stream_t stream);
 /* weight gradient: slabs = [sed_conv3x3_tc_wgrad_splits()][9][Cout][Cin] fp32 split-K partials;
  * sed_conv_unpack_wgrad sums them (fixed order) into the OIHW fp32 gradient. */
 int sed_conv3x3_tc_wgrad_splits(int B, int H, int W, int Cin, int Cout);
@@ -109,8 +117,11 @@ int sed_bn_bwd_partials(int C);
 int sed_bn_relu_pool_bwd_reduce(const void* y, const void* dA, int grad_is_f32, const float* scale,
                                 const float* shift, const float* mean, const float* invstd, int B, int H, int W,
                                 int C, int ph, int pw, float* partial, sed_stream_t stream);
+/* mean_for_gy: NULL when the second partial column holds sum(g*xhat) (sed_bn_relu_pool_bwd_reduce); the layer's
+ * batch mean when it holds sum(g*y) (sed_conv3x3_tc_dgrad_bnr): sum(g*xhat) = invstd*(sum(g*y) - mean*sum(g)). */
 int sed_bn_bwd_finalize(const float* partial, int P, int C, double count, const float* gamma, const float* invstd,
-                        float* dgamma, float* dbeta, int accumulate, float* coef, sed_stream_t stream);
+                        const float* mean_for_gy, float* dgamma, float* dbeta, int accumulate, float* coef,
+                        sed_stream_t stream);
 int sed_bn_relu_pool_bwd_apply(const void* y, const void* dA, int grad_is_f32, const float* scale, const float* shift,
                                const float* mean, const float* invstd, const float* coef, int B, int H, int W, int C,
                                int ph, int pw, void* dy, sed_stream_t stream);

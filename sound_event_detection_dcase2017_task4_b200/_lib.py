@@ -28,6 +28,7 @@ SIGNATURES = {
     'sed_conv_pack_weights': [P, I, I, P, P, P],
     'sed_conv3x3_tc_grid': [I, I, I, I, I],
     'sed_conv3x3_tc_fwd': [P, P, P, P, I, I, I, I, I, P],
+    'sed_conv3x3_tc_dgrad_bnr': [P, P, P, I, I, I, I, I, P, I, P, P, I, P, P],
     'sed_conv3x3_tc_wgrad_splits': [I, I, I, I, I],
     'sed_conv3x3_tc_wgrad': [P, P, P, I, I, I, I, I, P],
     'sed_conv_unpack_wgrad': [P, I, L, I, I, P, I, P],
@@ -37,7 +38,7 @@ SIGNATURES = {
     'sed_bn_relu_pool_fwd': [P, P, P, I, I, I, I, I, I, P, I, P],
     'sed_bn_bwd_partials': [I],
     'sed_bn_relu_pool_bwd_reduce': [P, P, I, P, P, P, P, I, I, I, I, I, I, P, P],
-    'sed_bn_bwd_finalize': [P, I, I, D, P, P, P, P, I, P, P],
+    'sed_bn_bwd_finalize': [P, I, I, D, P, P, P, P, P, I, P, P],
     'sed_bn_relu_pool_bwd_apply': [P, P, I, P, P, P, P, P, I, I, I, I, I, I, P, P],
     'sed_stat_partials': [],
     'sed_colstats_f32': [P, L, I, P, P],

@@ -40,6 +40,28 @@ def conv3x3(x, wpack, cout, want_stats=False):
     return (y, stats) if want_stats else y
 
 
+def conv3x3_dgrad_bnr(dy, wpack_dgrad, cin, y_below, st_below, pool):
+    """Data gradient fused with the first BN-backward pass of the layer below.
+
+    dy (B,H,W,Cout) bf16, wpack_dgrad [cin, 9*Cout] -> dx (B,H,W,cin) bf16 (= dA of the layer below) and
+    gy_partial (grid, 2, cin) fp32: per-CTA sums of g and g*y over that layer's raw output ``y_below``
+    (B, Hy, W*pool, cin), g = unpool(dx)/pool^2 * [bn(y) > 0]."""
+    assert dy.is_cuda and dy.dtype == torch.bfloat16 and dy.is_contiguous()
+    b, h, w, cout = dy.shape
+    assert wpack_dgrad.shape == (cin, 9 * cout) and wpack_dgrad.is_contiguous()
+    assert y_below.dtype == torch.bfloat16 and y_below.is_contiguous()
+    yb, hy, wy, cy = y_below.shape
+    assert yb == b and cy == cin and wy == w * pool and hy // pool == h, (y_below.shape, dy.shape, pool)
+    dx = torch.empty((b, h, w, cin), dtype=torch.bfloat16, device=dy.device)
+    with torch.cuda.device(dy.device):
+        grid = _lib.lib().sed_conv3x3_tc_grid(b, h, w, cout, cin)
+        partial = torch.empty((grid, 2, cin), dtype=torch.float32, device=dy.device)
+        _lib.call('sed_conv3x3_tc_dgrad_bnr', dy.data_ptr(), wpack_dgrad.data_ptr(), dx.data_ptr(), b, h, w, cout,
+                  cin, y_below.data_ptr(), hy, st_below.scale.data_ptr(), st_below.shift.data_ptr(), pool,
+                  partial.data_ptr(), _lib.stream_of(dy))
+    return dx, partial
+
+
 def conv3x3_wgrad(dy, x, out=None, accumulate=False):
     """dy (B,H,W,Cout) bf16, x (B,H,W,Cin) bf16 -> dW fp32 (Cout, Cin, 3, 3)."""
     assert dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16

@@ -180,12 +180,14 @@ __global__ void bn_relu_pool_bwd_reduce_kernel(const __nv_bfloat16* __restrict__
 
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int P, int C, double count,
                                        const float* __restrict__ gamma, const float* __restrict__ invstd,
+                                       const float* __restrict__ mean_for_gy,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
                                        float* __restrict__ coef /* [3][C]: gamma*invstd, mean(g), mean(g*xhat) */) {
   const int c = blockIdx.x * 32 + threadIdx.x;
   double s, sx;
   colsum2_block(partial, partial + C, P, 2LL * C, c, c < C, s, sx);
   if (threadIdx.y != 0 || c >= C) return;
+  if (mean_for_gy) sx = (double)invstd[c] * (sx - (double)mean_for_gy[c] * s);    // partials held sum(g*y)
   if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)sx : (float)sx;
   if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)s : (float)s;
   if (coef) {
@@ -669,10 +671,11 @@ int sed_bn_relu_pool_bwd_reduce(const void* y, const void* dA, int grad_is_f32, 
 }
 
 int sed_bn_bwd_finalize(const float* partial, int P, int C, double count, const float* gamma, const float* invstd,
-                        float* dgamma, float* dbeta, int accumulate, float* coef, sed_stream_t stream) {
+                        const float* mean_for_gy, float* dgamma, float* dbeta, int accumulate, float* coef,
+                        sed_stream_t stream) {
   SED_REQUIRE(partial && invstd && P >= 1 && C >= 1, "sed_bn_bwd_finalize: bad arguments");
   bn_bwd_finalize_kernel<<<ceil_div(C, 32), dim3(32, kColLanes), 0, (cudaStream_t)stream>>>(partial, P, C, count, gamma, invstd,
-                                                                             dgamma, dbeta, accumulate, coef);
+                                                                             mean_for_gy, dgamma, dbeta, accumulate, coef);
   SED_LAUNCH_CHECK("bn_bwd_finalize_kernel");
   return 0;
 }

@@ -71,9 +71,21 @@ struct HaloParams {
   int a_stages, b_stages;
   __nv_bfloat16* y;    // NHWC output
   float* stats;        // [gridDim.x][2][Cout] partial (sum, sumsq) or nullptr
+  // fused first pass of the BatchNorm+ReLU(+2x2 avg-pool) backward of the layer BELOW (kBnr kernels, data gradient):
+  // this kernel's output is that layer's dA; partials of sum(g) and sum(g*y), g = unpool(dA)/pool^2 * [bn(y) > 0]
+  const __nv_bfloat16* bnr_y;      // raw conv output of the layer below: [B][H*pool (+tail)][W*pool][Cout]
+  const float* bnr_scale;          // its BatchNorm scale / shift (relu mask = y*scale + shift > 0)
+  const float* bnr_shift;
+  int bnr_pool;                    // 1 or 2
+  int bnr_Hy;                      // rows of bnr_y per clip
 };
 
-template <int kN, int kMT, bool kResidentB>
+__device__ __forceinline__ void unpack8_bf16(const uint4& raw, float (&v)[8]) {
+  const float2 a = unpack_bf16x2(raw.x), b = unpack_bf16x2(raw.y), c = unpack_bf16x2(raw.z), d = unpack_bf16x2(raw.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+
+template <int kN, int kMT, bool kResidentB, bool kBnr>
 __global__ void __launch_bounds__(kHThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const HaloParams p) {
@@ -200,6 +212,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
+    // (setmaxnreg register re-allocation over 3 warpgroups was tried: ptxas then spills in every role -- kept at 10 warps)
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;              // which of the two warps of this quarter
     const int row = q * 32 + lane;
@@ -233,16 +246,46 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (acc * kMT + mt) * kN + c * 32, v);
           if (valid) {
             uint4* d4 = reinterpret_cast<uint4*>(p.y + (((long long)b * p.H + h) * p.W + r_w) * p.Cout + n_tile * kN + c * 32);
+            uint32_t pk[16];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 o;
-              o.x = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]);
-              o.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
-              o.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
-              o.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
-              d4[g] = o;
-            }
-            if (p.stats != nullptr) {
+            for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) d4[g] = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+            if (kBnr) {
+              // g uses the bf16-rounded dA that was just stored (what the second BN-backward pass will read back)
+              const int ch0 = n_tile * kN + c * 32;
+              const float4* sc4 = reinterpret_cast<const float4*>(p.bnr_scale + ch0);
+              const float4* sh4 = reinterpret_cast<const float4*>(p.bnr_shift + ch0);
+              const int pool = p.bnr_pool;
+              const float gscale = pool == 2 ? 0.25f : 1.0f;
+              const int Wy = p.W * pool;
+#pragma unroll 1
+              for (int win = 0; win < pool * pool; ++win) {
+                const int dh = win >> 1, dw = win & 1;
+                const uint4* yp = reinterpret_cast<const uint4*>(
+                    p.bnr_y + (((long long)b * p.bnr_Hy + h * pool + dh) * Wy + r_w * pool + dw) * p.Cout + ch0);
+                uint4 raw[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) raw[g] = __ldg(yp + g);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  float yv[8];
+                  unpack8_bf16(raw[g], yv);
+                  const float4 sa = __ldg(sc4 + 2 * g), sb = __ldg(sc4 + 2 * g + 1);
+                  const float4 ha = __ldg(sh4 + 2 * g), hb = __ldg(sh4 + 2 * g + 1);
+                  const float scv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+                  const float shv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) {
+                    const float2 d2 = unpack_bf16x2(pk[4 * g + (k >> 1)]);
+                    const float dv = ((k & 1) ? d2.y : d2.x) * gscale;
+                    const float gk = fmaf(yv[k], scv[k], shv[k]) > 0.f ? dv : 0.f;
+                    s_acc[8 * g + k] += gk;
+                    ss_acc[8 * g + k] = fmaf(gk, yv[k], ss_acc[8 * g + k]);
+                  }
+                }
+              }
+            } else if (p.stats != nullptr) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
                 s_acc[i] += v[i];
@@ -319,9 +362,9 @@ bool make_plan(int B, int H, int W, int Cin, int Cout, HaloPlan* q) {
   return true;
 }
 
-template <int kN, int kMT, bool kRes>
+template <int kN, int kMT, bool kRes, bool kBnr>
 int launch_halo(const CUtensorMap& ta, const CUtensorMap& tb, const HaloParams& p, const HaloPlan& q, cudaStream_t stream) {
-  auto kern = conv3x3_halo_kernel<kN, kMT, kRes>;
+  auto kern = conv3x3_halo_kernel<kN, kMT, kRes, kBnr>;
   SED_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, q.smem));
   kern<<<q.grid, kHThreads, q.smem, stream>>>(ta, tb, p);
   SED_LAUNCH_CHECK("conv3x3_halo_kernel");
@@ -341,17 +384,17 @@ int sed_conv3x3_tc_grid(int B, int H, int W, int Cin, int Cout) {
   return q.grid;
 }
 
-int sed_conv3x3_tc_fwd(const void* x, const void* wpack, void* y, float* stats_partial, int B, int H, int W,
-                       int Cin, int Cout, sed_stream_t stream) {
-  SED_REQUIRE(x && wpack && y, "sed_conv3x3_tc_fwd: null pointer");
-  SED_REQUIRE(B > 0 && H > 0, "sed_conv3x3_tc_fwd: empty batch");
-  SED_REQUIRE(W >= 8 && W <= 128 && 128 % W == 0, "sed_conv3x3_tc_fwd: W=%d must divide 128 and be >= 8", W);
-  SED_REQUIRE(Cin % 64 == 0 && Cin >= 64, "sed_conv3x3_tc_fwd: Cin=%d must be a multiple of 64", Cin);
-  SED_REQUIRE((Cout == 64 || Cout == 128 || Cout % 256 == 0) && Cout <= 512, "sed_conv3x3_tc_fwd: Cout=%d unsupported", Cout);
-  SED_REQUIRE(aligned(y, 16), "sed_conv3x3_tc_fwd: output must be 16-byte aligned");
+static int conv_halo_dispatch(const void* x, const void* wpack, void* y, float* stats_partial, int B, int H, int W,
+                              int Cin, int Cout, const void* bnr_y, const float* bnr_scale, const float* bnr_shift,
+                              int bnr_pool, int bnr_Hy, sed_stream_t stream, const char* who) {
+  SED_REQUIRE(x && wpack && y, "%s: null pointer", who);
+  SED_REQUIRE(B > 0 && H > 0, "%s: empty batch", who);
+  SED_REQUIRE(W >= 8 && W <= 128 && 128 % W == 0, "%s: W=%d must divide 128 and be >= 8", who, W);
+  SED_REQUIRE(Cin % 64 == 0 && Cin >= 64, "%s: Cin=%d must be a multiple of 64", who, Cin);
+  SED_REQUIRE((Cout == 64 || Cout == 128 || Cout % 256 == 0) && Cout <= 512, "%s: Cout=%d unsupported", who, Cout);
+  SED_REQUIRE(aligned(y, 16), "%s: output must be 16-byte aligned", who);
   HaloPlan q;
-  SED_REQUIRE(make_plan(B, H, W, Cin, Cout, &q), "sed_conv3x3_tc_fwd: no tiling for B=%d H=%d W=%d Cin=%d Cout=%d", B, H,
-              W, Cin, Cout);
+  SED_REQUIRE(make_plan(B, H, W, Cin, Cout, &q), "%s: no tiling for B=%d H=%d W=%d Cin=%d Cout=%d", who, B, H, W, Cin, Cout);
   HaloParams p;
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.bh = q.bh; p.rows_per_tile = q.rows_per_tile; p.tiles_h = q.tiles_h; p.tiles_n = q.tiles_n;
@@ -359,6 +402,9 @@ int sed_conv3x3_tc_fwd(const void* x, const void* wpack, void* y, float* stats_p
   p.a_stages = q.a_stages; p.b_stages = q.b_stages;
   p.y = reinterpret_cast<__nv_bfloat16*>(y);
   p.stats = stats_partial;
+  p.bnr_y = reinterpret_cast<const __nv_bfloat16*>(bnr_y);
+  p.bnr_scale = bnr_scale; p.bnr_shift = bnr_shift; p.bnr_pool = bnr_pool; p.bnr_Hy = bnr_Hy;
+  const bool bnr = bnr_y != nullptr;
 
   alignas(64) CUtensorMap ta, tb;
   {
@@ -374,10 +420,32 @@ int sed_conv3x3_tc_fwd(const void* x, const void* wpack, void* y, float* stats_p
     if (int rc = tc::make_tmap_bf16(&tb, wpack, 2, dims, strides, box, "conv weight map")) return rc;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  if (q.kN == 64 && q.resident) return launch_halo<64, 2, true>(ta, tb, p, q, s);
-  if (q.kN == 64) return launch_halo<64, 2, false>(ta, tb, p, q, s);
-  if (q.kN == 128) return launch_halo<128, 2, false>(ta, tb, p, q, s);
-  return launch_halo<256, 1, false>(ta, tb, p, q, s);
+#define SED_HALO(N, MT, RES) (bnr ? launch_halo<N, MT, RES, true>(ta, tb, p, q, s) : launch_halo<N, MT, RES, false>(ta, tb, p, q, s))
+  if (q.kN == 64 && q.resident) return SED_HALO(64, 2, true);
+  if (q.kN == 64) return SED_HALO(64, 2, false);
+  if (q.kN == 128) return SED_HALO(128, 2, false);
+  return SED_HALO(256, 1, false);
+#undef SED_HALO
+}
+
+int sed_conv3x3_tc_fwd(const void* x, const void* wpack, void* y, float* stats_partial, int B, int H, int W,
+                       int Cin, int Cout, sed_stream_t stream) {
+  return conv_halo_dispatch(x, wpack, y, stats_partial, B, H, W, Cin, Cout, nullptr, nullptr, nullptr, 0, 0, stream,
+                            "sed_conv3x3_tc_fwd");
+}
+
+int sed_conv3x3_tc_dgrad_bnr(const void* dy, const void* wpack_dgrad, void* dx, int B, int H, int W, int Cin, int Cout,
+                             const void* y_below, int Hy, const float* scale_below, const float* shift_below,
+                             int pool, float* partial, sed_stream_t stream) {
+  SED_REQUIRE(y_below && scale_below && shift_below && partial, "sed_conv3x3_tc_dgrad_bnr: null pointer");
+  SED_REQUIRE(pool == 1 || pool == 2, "sed_conv3x3_tc_dgrad_bnr: pool=%d must be 1 or 2", pool);
+  SED_REQUIRE(Hy / pool == H, "sed_conv3x3_tc_dgrad_bnr: y has %d rows per clip, expected %d..%d", Hy, H * pool,
+              H * pool + pool - 1);
+  SED_REQUIRE(aligned(y_below, 16) && aligned(scale_below, 16) && aligned(shift_below, 16),
+              "sed_conv3x3_tc_dgrad_bnr: y / scale / shift must be 16-byte aligned");
+  return conv_halo_dispatch(dy, wpack_dgrad, dx, partial, B, H, W, Cin, Cout, y_below, scale_below, shift_below, pool,
+                            Hy, stream,
+                            "sed_conv3x3_tc_dgrad_bnr");
 }
 
 }  // extern "C"

@@ -114,6 +114,12 @@ _SIDE_STREAMS = {}
 # no register room for a co-resident tensor-core CTA, so the kernels serialise anyway.  Off until the BN kernels are
 # made co-residency friendly.
 OVERLAP_WGRAD = False
+# Fold the reduction pass of each BatchNorm backward into the epilogue of the data-gradient kernel that produces its dA
+# (sed_conv3x3_tc_dgrad_bnr).  Correct (tests/test_gpu_conv.py) but measured SLOWER on B200 at batch 256
+# (tools/ab_step.py: 42.1 vs 40.1 ms/step): the 8 epilogue warps cannot hide the HBM latency of the y reads that the
+# dedicated 24-warp/SM reduction kernels stream at ~5 TB/s, and the epilogue is already the critical path of the
+# K = 576 layers.  Off.
+FUSE_BN_REDUCE = False
 
 
 def _side_stream(device):
@@ -141,9 +147,12 @@ def trunk_backward(ctx, dfeat, grad_of, overlap_wgrad=None):
     dev = dA.device
     main, side = _side_stream(dev) if overlap_wgrad else (None, None)
     used_side = False
-    for lc in reversed(ctx.layers):
+    gy_partial = None
+    for li in range(len(ctx.layers) - 1, -1, -1):
+        lc = ctx.layers[li]
         dy = ops.bn_relu_pool_bwd(lc.y, dA, lc.st, lc.bn, lc.ph, lc.pw, grad_of(lc.bn.weight),
-                                  grad_of(lc.bn.bias))
+                                  grad_of(lc.bn.bias), gy_partial=gy_partial)
+        gy_partial = None
         gw = grad_of(lc.conv.weight)
         if gw is not None:
             if overlap_wgrad:
@@ -161,7 +170,13 @@ def trunk_backward(ctx, dfeat, grad_of, overlap_wgrad=None):
         if lc.is_c1:
             dA = ops.conv_c1_dgrad(dy, lc.conv.weight)                 # (B, T, M) fp32
         else:
-            dA = tcconv.conv3x3(dy, lc.wd, lc.conv.weight.shape[1])    # bf16 NHWC
+            below = ctx.layers[li - 1]
+            cin = lc.conv.weight.shape[1]
+            if FUSE_BN_REDUCE and (below.ph, below.pw) in ((1, 1), (2, 2)) and below.y.shape[2] % below.pw == 0:
+                # the data gradient also produces the first pass of the BatchNorm backward of the layer below
+                dA, gy_partial = tcconv.conv3x3_dgrad_bnr(dy, lc.wd, cin, below.y, below.st, below.ph)
+            else:
+                dA = tcconv.conv3x3(dy, lc.wd, cin)                    # bf16 NHWC
         lc.y = lc.x_in = None
     g0w, g0b = grad_of(ctx.bn0.weight), grad_of(ctx.bn0.bias)
     if g0w is not None or g0b is not None:

@@ -10,6 +10,7 @@
 ``prepare()`` arranges ``sys.path`` so that
 
     models, losses, pytorch_utils          -> dropin/  (this package; seam B of SURVEY 8b)
+    data_generator                         -> dropin/  (memory-mapped clip store; HDF5 packs still work via h5py)
     torchlibrosa.{stft,augmentation}       -> dropin/torchlibrosa  (seam A; pytorch/models.py:10-11)
     evaluate                               -> <reference>/pytorch   (untouched, off the hot path)
     config, utilities, data_generator, ... -> <reference>/utils     (untouched)
@@ -22,7 +23,7 @@ import runpy
 import sys
 
 DROPIN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'dropin')
-SHADOWED = ('models', 'losses', 'pytorch_utils', 'torchlibrosa')
+SHADOWED = ('models', 'losses', 'pytorch_utils', 'torchlibrosa', 'data_generator')
 
 
 def prepare(reference_root):

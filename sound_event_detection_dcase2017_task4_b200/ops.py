@@ -64,21 +64,29 @@ def bn_relu_pool_fwd(y, st, ph, pw, out_f32=False):
     return out
 
 
-def bn_relu_pool_bwd(y, dA, st, bn, ph, pw, dgamma, dbeta):
+def bn_relu_pool_bwd(y, dA, st, bn, ph, pw, dgamma, dbeta, gy_partial=None):
     """Two-pass BN+ReLU+pool backward.  Writes bn parameter grads into dgamma/dbeta (fp32 (C,)
-    tensors, may be None) and returns dY (bf16, same shape as y)."""
+    tensors, may be None) and returns dY (bf16, same shape as y).
+
+    ``gy_partial``: (P, 2, C) partial sums of g and g*y already produced by the data-gradient kernel that wrote
+    ``dA`` (conv.conv3x3_dgrad_bnr); the reduction pass over y and dA is then skipped."""
     b, h, w, c = y.shape
     f32 = 1 if dA.dtype == F32 else 0
     with _dev(y):
-        P = _lib.lib().sed_bn_bwd_partials(c)
-        partial = _empty((P, 2, c), F32, y)
         coef = _empty((3, c), F32, y)
         s = stream_of(y)
-        call('sed_bn_relu_pool_bwd_reduce', y.data_ptr(), dA.data_ptr(), f32, st.scale.data_ptr(),
-             st.shift.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(), b, h, w, c, ph, pw,
-             partial.data_ptr(), s)
+        if gy_partial is None:
+            P = _lib.lib().sed_bn_bwd_partials(c)
+            partial = _empty((P, 2, c), F32, y)
+            call('sed_bn_relu_pool_bwd_reduce', y.data_ptr(), dA.data_ptr(), f32, st.scale.data_ptr(),
+                 st.shift.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(), b, h, w, c, ph, pw,
+                 partial.data_ptr(), s)
+            mean_for_gy = 0
+        else:
+            partial, P = gy_partial, gy_partial.shape[0]
+            mean_for_gy = st.mean.data_ptr()
         call('sed_bn_bwd_finalize', partial.data_ptr(), P, c, float(b * h * w), ptr(bn.weight),
-             st.invstd.data_ptr(), ptr(dgamma), ptr(dbeta), 0, coef.data_ptr(), s)
+             st.invstd.data_ptr(), mean_for_gy, ptr(dgamma), ptr(dbeta), 0, coef.data_ptr(), s)
         dy = _empty(y.shape, BF16, y)
         call('sed_bn_relu_pool_bwd_apply', y.data_ptr(), dA.data_ptr(), f32, st.scale.data_ptr(),
              st.shift.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(), coef.data_ptr(), b, h, w, c,
@@ -121,7 +129,7 @@ def bn0_bwd(dout, logmel, st, bn, t_stripes, f_stripes, lam, dgamma, dbeta):
              st.invstd.data_ptr(), ptr(t_stripes), nt, ptr(f_stripes), nf, ptr(lam), b2, t, m,
              partial.data_ptr(), s)
         # bn0: d(gamma) = sum d*xhat, d(beta) = sum d  (no dX needed: the waveform takes no gradient)
-        call('sed_bn_bwd_finalize', partial.data_ptr(), P, m, float(b2 * t), 0, st.invstd.data_ptr(),
+        call('sed_bn_bwd_finalize', partial.data_ptr(), P, m, float(b2 * t), 0, st.invstd.data_ptr(), 0,
              ptr(dgamma), ptr(dbeta), 0, 0, s)
 
 

@@ -69,3 +69,42 @@ def test_conv_wgrad(B, H, W, Cin, Cout):
     ref = wr.grad
     err = (dw - ref).abs().max().item()
     assert err <= 1e-3 * ref.abs().max().item() + 1e-3, err
+
+
+@pytest.mark.parametrize('B,H,W,Cin,Cout,pool', [
+    (2, 101, 64, 64, 64, 1),      # block1.conv2 dgrad + bn1 reduce (resident-weight kernel)
+    (3, 50, 32, 128, 64, 2),      # block2.conv1 dgrad + block1.bn2 reduce through the 2x2 pool (y has 101 rows: tail)
+    (2, 50, 32, 128, 128, 1),     # block2.conv2 dgrad + bn1 reduce
+    (2, 25, 16, 256, 128, 2),     # block3.conv1 dgrad + block2.bn2 reduce (y has 50 rows)
+    (2, 12, 8, 512, 256, 2),      # block4.conv1 dgrad + block3.bn2 reduce (N = 256 kernel, y has 25 rows: tail)
+    (1, 125, 8, 512, 512, 1),     # block4.conv2 dgrad + bn1 reduce
+])
+def test_conv_dgrad_with_fused_bn_reduce(B, H, W, Cin, Cout, pool):
+    """sed_conv3x3_tc_dgrad_bnr: same dX as the plain data gradient, and partial sums of g and g*y for the layer
+    below (g = unpool(dX)/pool^2 * relu-mask) equal to a PyTorch fp32 evaluation on the stored bf16 dX."""
+    from sound_event_detection_dcase2017_task4_b200 import conv
+    cin_eff = Cout                                    # channels of the gradient being produced = channels of y below
+    dy = _rand((B, H, W, Cin), 11).cuda().to(torch.bfloat16)
+    w = (_rand((Cin, cin_eff, 3, 3), 12) * (2.0 / (9 * Cin)) ** 0.5).cuda()      # layer weight (Cout=Cin here, Cin=cin_eff)
+    _, wd = conv.pack_weights(w)
+    Hy = H * pool + (1 if pool == 2 and H % 2 == 0 else 0)
+    y = _rand((B, Hy, W * pool, cin_eff), 13).cuda().to(torch.bfloat16)
+
+    class St(object):
+        pass
+    st = St()
+    st.scale = (0.5 + torch.rand(cin_eff, device='cuda'))
+    st.scale[::3] *= -1.0
+    st.shift = torch.randn(cin_eff, device='cuda') * 0.3
+    dx_plain = conv.conv3x3(dy, wd, cin_eff)
+    dx, partial = conv.conv3x3_dgrad_bnr(dy, wd, cin_eff, y, st, pool)
+    assert torch.equal(dx, dx_plain)
+    g = dx.float()
+    if pool == 2:
+        g = g.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2) * 0.25
+    yy = y.float()[:, :H * pool]
+    g = g * ((yy * st.scale + st.shift) > 0)
+    want = torch.stack([g.double().sum(dim=(0, 1, 2)), (g.double() * yy.double()).sum(dim=(0, 1, 2))])
+    got = partial.double().sum(dim=0)
+    scale = want.abs().max(dim=1, keepdim=True).values + 1e-6
+    assert ((got - want).abs() / scale).max().item() <= 2e-4
