@@ -163,7 +163,6 @@ constexpr int kPB = 32;            // batch rows per group
 constexpr int kPJ = 32;            // hidden units per CTA
 constexpr int kPGroup = kPH / kPJ; // 8 CTAs per group
 constexpr int kPThreads = 256;
-constexpr int kPLdW = kPH + 4;
 
 // All CTAs of a group arrive; everyone leaves once `target` arrivals have been counted.  Writes made by any
 // thread of the CTA before the call are visible to every thread of the group after it (bar.sync, then
@@ -188,168 +187,262 @@ struct GruPersist {
   int B, T, b_base;
 };
 
+// ---- warp-level tensor-core pieces of the persistent kernels ----------------------------------------------------
+// The recurrent products are tiny per CTA and per step (32 x 96 x 256 forward, 32 x 32 x 768 backward) and sit on a
+// 125-step dependency chain, so they run as warp-level mma.sync.m16n8k16 tiles straight out of shared memory (a
+// tcgen05 tile would need M >= 64 rows and a TMEM round trip per step).  fp32 operands are split into bf16 hi + lo
+// parts and three products are accumulated (hi*hi + lo*hi + hi*lo): fp32-class accuracy on the bf16 pipe.
+__device__ __forceinline__ void mma_bf16_m16n8k16(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  const float h0 = __bfloat162float(__float2bfloat16_rn(v0)), h1 = __bfloat162float(__float2bfloat16_rn(v1));
+  hi = pack_bf16x2(h0, h1);
+  lo = pack_bf16x2(v0 - h0, v1 - h1);
+}
+// fp32 row-major [rows][cols] (global, read through L2) -> bf16 hi / lo shared tiles with row stride `ld` elements
+__device__ __forceinline__ void stage_split(const float* __restrict__ src, long long src_stride, int rows, int cols,
+                                            bool have, int valid_rows, __nv_bfloat16* __restrict__ s_hi,
+                                            __nv_bfloat16* __restrict__ s_lo, int ld, int tid, int nthreads) {
+  const int c4n = cols >> 2;
+  for (int i = tid; i < rows * c4n; i += nthreads) {
+    const int r = i / c4n, c4 = i - r * c4n;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (have && r < valid_rows) v = __ldcg(reinterpret_cast<const float4*>(src + r * src_stride + c4 * 4));
+    uint32_t h0, l0, h1, l1;
+    split2(v.x, v.y, h0, l0);
+    split2(v.z, v.w, h1, l1);
+    *reinterpret_cast<uint2*>(s_hi + r * ld + c4 * 4) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(s_lo + r * ld + c4 * 4) = make_uint2(l0, l1);
+  }
+}
+constexpr int kLdK = kPH + 8;          // bf16 row stride of the K = 256 tiles (528 B: conflict-free fragment loads)
+constexpr int kLdG = 3 * kPH + 8;      // bf16 row stride of the K = 768 tiles
+
+// Forward.  CTA r of a group owns hidden units [32r, 32r+32) of 32 batch rows: a 32 x 96 x 256 product per step
+// (gate columns ordered r | z | n).  Warp w: batch rows 16*(w&1).., unit octet w>>1, i.e. the three n-tiles
+// {o, 4+o, 8+o}: every thread ends up with r, z, n pre-activations of the SAME (row, unit) pairs, does the gate math
+// in registers and keeps its four h values for the next step's z*h term.
 __global__ void __launch_bounds__(kPThreads, 1)
 gru_fwd_persistent_kernel(const float* __restrict__ Gx, const float* __restrict__ Whh, const float* __restrict__ bhh,
                           float* out, float* __restrict__ gates, GruPersist q) {
-  extern __shared__ __align__(16) float smem[];
-  float* sW = smem;                              // [3*kPJ][kPLdW]
-  float* sH = smem + 3 * kPJ * kPLdW;            // [kPB][kPH]   h_{t-1} of this group's rows
+  extern __shared__ __align__(16) uint8_t smem_gru[];
+  __nv_bfloat16* sWh = reinterpret_cast<__nv_bfloat16*>(smem_gru);      // [96][kLdK]  W_hh slice, hi
+  __nv_bfloat16* sWl = sWh + 3 * kPJ * kLdK;                            //             lo
+  __nv_bfloat16* sHh = sWl + 3 * kPJ * kLdK;                            // [32][kLdK]  h_{t-1}, hi
+  __nv_bfloat16* sHl = sHh + kPB * kLdK;                                //             lo
   constexpr int H = kPH;
   const int B = q.B, T = q.T;
   const int j0 = blockIdx.x * kPJ, b0 = q.b_base + blockIdx.y * kPB, d = blockIdx.z;
   unsigned int* ctr = q.sync_ctr + (blockIdx.y * 2 + d);
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gid = lane >> 2, tig = lane & 3;
   const float* W = Whh + (long long)d * 3 * H * H;
-  for (int i = tid; i < 3 * kPJ * (H / 4); i += kPThreads) {
-    const int row = i / (H / 4), k4 = i % (H / 4);
-    const int g = row / kPJ, jl = row % kPJ;
-    *reinterpret_cast<float4*>(sW + row * kPLdW + k4 * 4) =
-        *reinterpret_cast<const float4*>(W + ((long long)(g * H + j0 + jl)) * H + k4 * 4);
-  }
-  const int jl = tid & 31, bl0 = (tid >> 5) * 4;                   // thread tile: 4 batch rows x 1 hidden unit
+  for (int g = 0; g < 3; ++g)          // rows g*32 .. g*32+31 of the slice = W_hh rows g*H + j0 ..
+    stage_split(W + ((long long)g * H + j0) * H, H, kPJ, H, true, kPJ, sWh + g * kPJ * kLdK, sWl + g * kPJ * kLdK, kLdK,
+                tid, kPThreads);
+  const int mt = warp & 1, oct = warp >> 1;
+  const int row0 = mt * 16 + gid;                                       // this thread's rows: row0, row0 + 8
+  const int jl = oct * 8 + tig * 2;                                     // its units: j0 + jl, j0 + jl + 1
   const int j = j0 + jl;
   const float* bh = bhh + d * 3 * H;
-  const float bh_r = bh[j], bh_z = bh[H + j], bh_n = bh[2 * H + j];
-  const float* wr = sW + (0 * kPJ + jl) * kPLdW;
-  const float* wz = sW + (1 * kPJ + jl) * kPLdW;
-  const float* wn = sW + (2 * kPJ + jl) * kPLdW;
+  // (scalar loads: a bias may be a 4-byte-aligned view into a flat parameter buffer)
+  const float2 bh_r = make_float2(bh[j], bh[j + 1]), bh_z = make_float2(bh[H + j], bh[H + j + 1]),
+               bh_n = make_float2(bh[2 * H + j], bh[2 * H + j + 1]);
+  float hprev[2][2] = {{0.f, 0.f}, {0.f, 0.f}};                         // [row][unit]
   for (int s = 0; s < T; ++s) {
     const int tt = d == 0 ? s : T - 1 - s;
     const int tp = d == 0 ? tt - 1 : tt + 1;
-    // this step's input projections: issued now, consumed after the recurrent matmul
-    float gxr[4], gxz[4], gxn[4];
+    // this step's input projections: issued now, consumed after the recurrent product
+    float2 gx[2][3];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int b = b0 + bl0 + i;
-      gxr[i] = gxz[i] = gxn[i] = 0.f;
+    for (int rr = 0; rr < 2; ++rr) {
+      const int b = b0 + row0 + rr * 8;
+#pragma unroll
+      for (int g = 0; g < 3; ++g) gx[rr][g] = make_float2(0.f, 0.f);
       if (b < B) {
-        const float* gx = Gx + (((long long)b * T + tt) * 2 + d) * 3 * H;
-        gxr[i] = __ldg(gx + j); gxz[i] = __ldg(gx + H + j); gxn[i] = __ldg(gx + 2 * H + j);
+        const float* gp = Gx + (((long long)b * T + tt) * 2 + d) * 3 * H + j;
+#pragma unroll
+        for (int g = 0; g < 3; ++g) gx[rr][g] = __ldg(reinterpret_cast<const float2*>(gp + g * H));
       }
     }
-    if (s > 0) group_barrier(ctr, (unsigned int)(kPGroup * s));     // h_{t-1} of all 8 CTAs is in L2
+    if (s > 0) group_barrier(ctr, (unsigned int)(kPGroup * s));         // h_{t-1} of all 8 CTAs is in L2
     else __syncthreads();
-    for (int i = tid; i < kPB * (H / 4); i += kPThreads) {
-      const int bl = i / (H / 4), k4 = i % (H / 4);
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (s > 0 && b0 + bl < B)
-        v = __ldcg(reinterpret_cast<const float4*>(out + ((long long)(b0 + bl) * T + tp) * 2 * H + d * H + k4 * 4));
-      *reinterpret_cast<float4*>(sH + bl * H + k4 * 4) = v;
-    }
+    stage_split(out + ((long long)b0 * T + tp) * 2 * H + d * H, (long long)T * 2 * H, kPB, H, s > 0, B - b0, sHh, sHl,
+                kLdK, tid, kPThreads);
     __syncthreads();
-    float ar[4], az[4], an[4];
+    float acc[3][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) ar[i] = az[i] = an[i] = 0.f;
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[g][i] = 0.f;
+    const __nv_bfloat16* ah = sHh + row0 * kLdK + tig * 2;
+    const __nv_bfloat16* al = sHl + row0 * kLdK + tig * 2;
+    const int brow = oct * 8 + gid;                                     // B fragment row (n index) within a gate block
 #pragma unroll 4
-    for (int k = 0; k < H; k += 4) {
-      const float4 r4 = *reinterpret_cast<const float4*>(wr + k);
-      const float4 z4 = *reinterpret_cast<const float4*>(wz + k);
-      const float4 n4 = *reinterpret_cast<const float4*>(wn + k);
+    for (int k0 = 0; k0 < H; k0 += 16) {
+      uint32_t a_hi[4], a_lo[4];
+      a_hi[0] = *reinterpret_cast<const uint32_t*>(ah + k0);
+      a_hi[1] = *reinterpret_cast<const uint32_t*>(ah + 8 * kLdK + k0);
+      a_hi[2] = *reinterpret_cast<const uint32_t*>(ah + k0 + 8);
+      a_hi[3] = *reinterpret_cast<const uint32_t*>(ah + 8 * kLdK + k0 + 8);
+      a_lo[0] = *reinterpret_cast<const uint32_t*>(al + k0);
+      a_lo[1] = *reinterpret_cast<const uint32_t*>(al + 8 * kLdK + k0);
+      a_lo[2] = *reinterpret_cast<const uint32_t*>(al + k0 + 8);
+      a_lo[3] = *reinterpret_cast<const uint32_t*>(al + 8 * kLdK + k0 + 8);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 h4 = *reinterpret_cast<const float4*>(sH + (bl0 + i) * H + k);
-        ar[i] = fmaf(h4.x, r4.x, ar[i]); ar[i] = fmaf(h4.y, r4.y, ar[i]); ar[i] = fmaf(h4.z, r4.z, ar[i]); ar[i] = fmaf(h4.w, r4.w, ar[i]);
-        az[i] = fmaf(h4.x, z4.x, az[i]); az[i] = fmaf(h4.y, z4.y, az[i]); az[i] = fmaf(h4.z, z4.z, az[i]); az[i] = fmaf(h4.w, z4.w, az[i]);
-        an[i] = fmaf(h4.x, n4.x, an[i]); an[i] = fmaf(h4.y, n4.y, an[i]); an[i] = fmaf(h4.z, n4.z, an[i]); an[i] = fmaf(h4.w, n4.w, an[i]);
+      for (int g = 0; g < 3; ++g) {
+        const __nv_bfloat16* wh = sWh + (g * kPJ + brow) * kLdK + k0 + tig * 2;
+        const __nv_bfloat16* wl = sWl + (g * kPJ + brow) * kLdK + k0 + tig * 2;
+        uint32_t b_hi[2], b_lo[2];
+        b_hi[0] = *reinterpret_cast<const uint32_t*>(wh);
+        b_hi[1] = *reinterpret_cast<const uint32_t*>(wh + 8);
+        b_lo[0] = *reinterpret_cast<const uint32_t*>(wl);
+        b_lo[1] = *reinterpret_cast<const uint32_t*>(wl + 8);
+        mma_bf16_m16n8k16(acc[g], a_hi, b_hi);
+        mma_bf16_m16n8k16(acc[g], a_lo, b_hi);
+        mma_bf16_m16n8k16(acc[g], a_hi, b_lo);
       }
     }
+    // accumulator element i of a thread: row = row0 + 8*(i>>1), unit = j + (i&1)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int b = b0 + bl0 + i;
+    for (int rr = 0; rr < 2; ++rr) {
+      const int b = b0 + row0 + rr * 8;
       if (b < B) {
-        const float ghn = an[i] + bh_n;
-        const float r = sigm(gxr[i] + ar[i] + bh_r);
-        const float z = sigm(gxz[i] + az[i] + bh_z);
-        const float n = tanhf(gxn[i] + r * ghn);
-        const float hp = sH[(bl0 + i) * H + j];
-        out[((long long)b * T + tt) * 2 * H + d * H + j] = (1.f - z) * n + z * hp;
-        float* gs = gates + (((long long)b * T + tt) * 2 + d) * 4 * H;
-        gs[j] = r; gs[H + j] = z; gs[2 * H + j] = n; gs[3 * H + j] = ghn;
+        float hn[2], rv[2], zv[2], nv[2], gv[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int i = rr * 2 + u;
+          const float ghn = acc[2][i] + (u ? bh_n.y : bh_n.x);
+          const float r = sigm((u ? gx[rr][0].y : gx[rr][0].x) + acc[0][i] + (u ? bh_r.y : bh_r.x));
+          const float z = sigm((u ? gx[rr][1].y : gx[rr][1].x) + acc[1][i] + (u ? bh_z.y : bh_z.x));
+          const float n = tanhf((u ? gx[rr][2].y : gx[rr][2].x) + r * ghn);
+          hn[u] = (1.f - z) * n + z * hprev[rr][u];
+          rv[u] = r; zv[u] = z; nv[u] = n; gv[u] = ghn;
+          hprev[rr][u] = hn[u];
+        }
+        *reinterpret_cast<float2*>(out + ((long long)b * T + tt) * 2 * H + d * H + j) = make_float2(hn[0], hn[1]);
+        float* gs = gates + (((long long)b * T + tt) * 2 + d) * 4 * H + j;
+        *reinterpret_cast<float2*>(gs) = make_float2(rv[0], rv[1]);
+        *reinterpret_cast<float2*>(gs + H) = make_float2(zv[0], zv[1]);
+        *reinterpret_cast<float2*>(gs + 2 * H) = make_float2(nv[0], nv[1]);
+        *reinterpret_cast<float2*>(gs + 3 * H) = make_float2(gv[0], gv[1]);
       }
     }
     // (the next iteration's barrier orders these stores before any other CTA's read, and its leading
-    //  __syncthreads orders this step's sH reads before the refill)
+    //  __syncthreads orders this step's shared-memory reads before the refill)
   }
 }
 
 // BPTT in one cooperative launch, same grouping.  CTA r owns hidden units / W_hh columns [32r, 32r+32): it
 // turns dh of its own units into the gate gradients (which it stores to dGx / dGh -- needed by the
 // weight-gradient GEMMs anyway), meets the group, reads the group's full dGh rows back from L2, and computes
-// its own 32 columns of dh_prev = dGh . W_hh + dh * z, which never leave its registers.
+// its own 32 columns of dh_prev = dGh . W_hh + dh * z (a 32 x 32 x 768 product on the warp-level MMA path), which
+// never leave its registers: the thread that owns accumulator element (row, unit) is the one that consumes it.
 __global__ void __launch_bounds__(kPThreads, 1)
 gru_bwd_persistent_kernel(const float* __restrict__ dout, const float* __restrict__ out, const float* __restrict__ gates,
                           const float* __restrict__ Whh, float* __restrict__ dGx, float* dGh,
                           float* __restrict__ Hprev, GruPersist q) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(16) uint8_t smem_gru[];
+  __nv_bfloat16* sDh = reinterpret_cast<__nv_bfloat16*>(smem_gru);      // [32][kLdG]  dGh rows of the group, hi
+  __nv_bfloat16* sDl = sDh + kPB * kLdG;                                //             lo
+  __nv_bfloat16* sWh = sDl + kPB * kLdG;                                // [32][kLdG]  W_hh[:, k0:k0+32]^T, hi
+  __nv_bfloat16* sWl = sWh + kPJ * kLdG;                                //             lo
   constexpr int H = kPH;
   const int B = q.B, T = q.T;
-  float* sD = smem;                                     // [kPB][3H]  dGh rows of the group
-  float* sW = sD + kPB * 3 * H;                         // [3H][kPJ]  W_hh[:, k0:k0+32]
   const int k0 = blockIdx.x * kPJ, b0 = q.b_base + blockIdx.y * kPB, d = blockIdx.z;
   unsigned int* ctr = q.sync_ctr + (blockIdx.y * 2 + d);
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gid = lane >> 2, tig = lane & 3;
   const float* W = Whh + (long long)d * 3 * H * H;
-  for (int i = tid; i < 3 * H * (kPJ / 4); i += kPThreads) {
-    const int row = i / (kPJ / 4), c4 = i % (kPJ / 4);
-    *reinterpret_cast<float4*>(sW + row * kPJ + c4 * 4) =
-        *reinterpret_cast<const float4*>(W + (long long)row * H + k0 + c4 * 4);
+  for (int i = tid; i < 3 * H * kPJ; i += kPThreads) {                  // transposed slice: sW[kl][row] = W[row][k0 + kl]
+    const int row = i / kPJ, kl = i - row * kPJ;
+    const float v = W[(long long)row * H + k0 + kl];
+    const float hi = __bfloat162float(__float2bfloat16_rn(v));
+    sWh[kl * kLdG + row] = __float2bfloat16_rn(hi);
+    sWl[kl * kLdG + row] = __float2bfloat16_rn(v - hi);
   }
-  const int kl = tid & 31, bl0 = (tid >> 5) * 4;        // thread tile: 4 batch rows x 1 hidden unit (j = k0 + kl)
-  const int j = k0 + kl;
-  float carry[4] = {0.f, 0.f, 0.f, 0.f};                // dh flowing back from the later time step
+  const int mt = warp & 1, oct = warp >> 1;
+  const int row0 = mt * 16 + gid;
+  const int j = k0 + oct * 8 + tig * 2;                                 // this thread's units: j, j + 1
+  float carry[2][2] = {{0.f, 0.f}, {0.f, 0.f}};                         // dh flowing back from the later time step
   for (int bs = 0; bs < T; ++bs) {
     const int tt = d == 0 ? T - 1 - bs : bs;
     const int tp = d == 0 ? tt - 1 : tt + 1;
     const bool has_prev = tp >= 0 && tp < T;
-    float dhz[4];
+    float dhz[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int b = b0 + bl0 + i;
-      dhz[i] = 0.f;
+    for (int rr = 0; rr < 2; ++rr) {
+      const int b = b0 + row0 + rr * 8;
       if (b < B) {
         const long long bt = (long long)b * T + tt;
-        const float* gs = gates + (bt * 2 + d) * 4 * H;
-        const float r = __ldg(gs + j), z = __ldg(gs + H + j), n = __ldg(gs + 2 * H + j), ghn = __ldg(gs + 3 * H + j);
-        const float hp = has_prev ? __ldg(out + ((long long)b * T + tp) * 2 * H + d * H + j) : 0.f;
-        const float dh = __ldg(dout + bt * 2 * H + d * H + j) + carry[i];
-        const float dn_pre = dh * (1.f - z) * (1.f - n * n);
-        const float dz_pre = dh * (hp - n) * z * (1.f - z);
-        const float dr_pre = dn_pre * ghn * r * (1.f - r);
-        dhz[i] = dh * z;
-        float* gx = dGx + (bt * 2 + d) * 3 * H;
-        float* gh = dGh + (bt * 2 + d) * 3 * H;
-        gx[j] = dr_pre; gx[H + j] = dz_pre; gx[2 * H + j] = dn_pre;
-        gh[j] = dr_pre; gh[H + j] = dz_pre; gh[2 * H + j] = dn_pre * r;
-        Hprev[(bt * 2 + d) * H + j] = hp;
+        const float* gs = gates + (bt * 2 + d) * 4 * H + j;
+        const float2 r2 = __ldg(reinterpret_cast<const float2*>(gs)), z2 = __ldg(reinterpret_cast<const float2*>(gs + H));
+        const float2 n2 = __ldg(reinterpret_cast<const float2*>(gs + 2 * H)),
+                     g2 = __ldg(reinterpret_cast<const float2*>(gs + 3 * H));
+        float2 hp2 = make_float2(0.f, 0.f);
+        if (has_prev) hp2 = __ldg(reinterpret_cast<const float2*>(out + ((long long)b * T + tp) * 2 * H + d * H + j));
+        const float2 do2 = __ldg(reinterpret_cast<const float2*>(dout + bt * 2 * H + d * H + j));
+        float drp[2], dzp[2], dnp[2], dnr[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const float r = u ? r2.y : r2.x, z = u ? z2.y : z2.x, n = u ? n2.y : n2.x, ghn = u ? g2.y : g2.x;
+          const float hp = u ? hp2.y : hp2.x;
+          const float dh = (u ? do2.y : do2.x) + carry[rr][u];
+          dnp[u] = dh * (1.f - z) * (1.f - n * n);
+          dzp[u] = dh * (hp - n) * z * (1.f - z);
+          drp[u] = dnp[u] * ghn * r * (1.f - r);
+          dnr[u] = dnp[u] * r;
+          dhz[rr][u] = dh * z;
+        }
+        float* gx = dGx + (bt * 2 + d) * 3 * H + j;
+        float* gh = dGh + (bt * 2 + d) * 3 * H + j;
+        *reinterpret_cast<float2*>(gx) = make_float2(drp[0], drp[1]);
+        *reinterpret_cast<float2*>(gx + H) = make_float2(dzp[0], dzp[1]);
+        *reinterpret_cast<float2*>(gx + 2 * H) = make_float2(dnp[0], dnp[1]);
+        *reinterpret_cast<float2*>(gh) = make_float2(drp[0], drp[1]);
+        *reinterpret_cast<float2*>(gh + H) = make_float2(dzp[0], dzp[1]);
+        *reinterpret_cast<float2*>(gh + 2 * H) = make_float2(dnr[0], dnr[1]);
+        *reinterpret_cast<float2*>(Hprev + (bt * 2 + d) * H + j) = hp2;
       }
     }
     if (bs == T - 1) break;                              // dh of the step before the first is not needed
     group_barrier(ctr, (unsigned int)(kPGroup * (bs + 1)));   // every CTA's dGh slice of this step is in L2
-    for (int i = tid; i < kPB * (3 * H / 4); i += kPThreads) {
-      const int bl = i / (3 * H / 4), c4 = i % (3 * H / 4);
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (b0 + bl < B)
-        v = __ldcg(reinterpret_cast<const float4*>(dGh + (((long long)(b0 + bl) * T + tt) * 2 + d) * 3 * H + c4 * 4));
-      *reinterpret_cast<float4*>(sD + bl * 3 * H + c4 * 4) = v;
-    }
+    stage_split(dGh + (((long long)b0 * T + tt) * 2 + d) * 3 * H, (long long)T * 2 * 3 * H, kPB, 3 * H, true, B - b0,
+                sDh, sDl, kLdG, tid, kPThreads);
     __syncthreads();
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 2
-    for (int row = 0; row < 3 * H; row += 4) {
-      const float w0 = sW[(row + 0) * kPJ + kl], w1 = sW[(row + 1) * kPJ + kl];
-      const float w2 = sW[(row + 2) * kPJ + kl], w3 = sW[(row + 3) * kPJ + kl];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 d4 = *reinterpret_cast<const float4*>(sD + (bl0 + i) * 3 * H + row);
-        acc[i] = fmaf(d4.x, w0, acc[i]);
-        acc[i] = fmaf(d4.y, w1, acc[i]);
-        acc[i] = fmaf(d4.z, w2, acc[i]);
-        acc[i] = fmaf(d4.w, w3, acc[i]);
-      }
+    const __nv_bfloat16* ah = sDh + row0 * kLdG + tig * 2;
+    const __nv_bfloat16* al = sDl + row0 * kLdG + tig * 2;
+    const __nv_bfloat16* wh = sWh + (oct * 8 + gid) * kLdG + tig * 2;
+    const __nv_bfloat16* wl = sWl + (oct * 8 + gid) * kLdG + tig * 2;
+#pragma unroll 4
+    for (int kk = 0; kk < 3 * H; kk += 16) {
+      uint32_t a_hi[4], a_lo[4], b_hi[2], b_lo[2];
+      a_hi[0] = *reinterpret_cast<const uint32_t*>(ah + kk);
+      a_hi[1] = *reinterpret_cast<const uint32_t*>(ah + 8 * kLdG + kk);
+      a_hi[2] = *reinterpret_cast<const uint32_t*>(ah + kk + 8);
+      a_hi[3] = *reinterpret_cast<const uint32_t*>(ah + 8 * kLdG + kk + 8);
+      a_lo[0] = *reinterpret_cast<const uint32_t*>(al + kk);
+      a_lo[1] = *reinterpret_cast<const uint32_t*>(al + 8 * kLdG + kk);
+      a_lo[2] = *reinterpret_cast<const uint32_t*>(al + kk + 8);
+      a_lo[3] = *reinterpret_cast<const uint32_t*>(al + 8 * kLdG + kk + 8);
+      b_hi[0] = *reinterpret_cast<const uint32_t*>(wh + kk);
+      b_hi[1] = *reinterpret_cast<const uint32_t*>(wh + kk + 8);
+      b_lo[0] = *reinterpret_cast<const uint32_t*>(wl + kk);
+      b_lo[1] = *reinterpret_cast<const uint32_t*>(wl + kk + 8);
+      mma_bf16_m16n8k16(acc, a_hi, b_hi);
+      mma_bf16_m16n8k16(acc, a_lo, b_hi);
+      mma_bf16_m16n8k16(acc, a_hi, b_lo);
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) carry[i] = acc[i] + dhz[i];
-    // (the next barrier's leading __syncthreads orders these sD reads before the refill)
+    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+      for (int u = 0; u < 2; ++u) carry[rr][u] = acc[rr * 2 + u] + dhz[rr][u];
+    // (the next barrier's leading __syncthreads orders these shared-memory reads before the refill)
   }
 }
 
@@ -435,7 +528,7 @@ int sed_gru_fwd(const float* gx, const float* w_hh, const float* b_hh, float* ou
   SED_REQUIRE(H % kHT == 0 && H % 4 == 0 && H <= 512, "sed_gru_fwd: hidden size %d unsupported", H);
   if (B == 0 || T == 0) return 0;
   if (H == kPH && sync_ws != nullptr) {
-    const size_t psmem = sizeof(float) * (size_t)(3 * kPJ * kPLdW + kPB * kPH);
+    const size_t psmem = sizeof(__nv_bfloat16) * (size_t)(2 * 3 * kPJ * kLdK + 2 * kPB * kLdK);
     return launch_gru_persistent((const void*)gru_fwd_persistent_kernel, "sed_gru_fwd", psmem, B, T,
                                  reinterpret_cast<unsigned int*>(sync_ws), (cudaStream_t)stream, [&](void** a) {
                                    a[0] = (void*)&gx; a[1] = (void*)&w_hh; a[2] = (void*)&b_hh; a[3] = (void*)&out; a[4] = (void*)&gates;
@@ -459,7 +552,7 @@ int sed_gru_bwd(const float* dout, const float* out, const float* gates, const f
   if (B == 0 || T == 0) return 0;
   if (H == kPH) {
     // the carry scratch is not needed (dh never leaves registers); its head holds the group counters
-    const size_t psmem = sizeof(float) * (size_t)(kPB * 3 * kPH + 3 * kPH * kPJ);
+    const size_t psmem = sizeof(__nv_bfloat16) * (size_t)(2 * kPB * kLdG + 2 * kPJ * kLdG);
     return launch_gru_persistent((const void*)gru_bwd_persistent_kernel, "sed_gru_bwd", psmem, B, T,
                                  reinterpret_cast<unsigned int*>(carry), (cudaStream_t)stream, [&](void** a) {
                                    a[0] = (void*)&dout; a[1] = (void*)&out; a[2] = (void*)&gates; a[3] = (void*)&w_hh;

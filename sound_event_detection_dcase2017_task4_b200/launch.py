@@ -13,7 +13,7 @@
     data_generator                         -> dropin/  (memory-mapped clip store; HDF5 packs still work via h5py)
     torchlibrosa.{stft,augmentation}       -> dropin/torchlibrosa  (seam A; pytorch/models.py:10-11)
     evaluate                               -> <reference>/pytorch   (untouched, off the hot path)
-    config, utilities, data_generator, ... -> <reference>/utils     (untouched)
+    config, utilities, vad, ...            -> <reference>/utils     (untouched)
 
 and ``main()`` then executes the reference file's bytes with ``runpy`` -- nothing under the reference tree
 is edited, copied or monkey-patched.
