@@ -301,16 +301,38 @@ bn_relu_pool_fwd_rows_kernel(const __nv_bfloat16* __restrict__ y, const float* _
   }
 }
 
-// backward pass 1 over input rows (b, h): partial sums of g and g*xhat per channel
-template <int kPool, bool kGradF32>
+// ---- un-pooled (1x1) layers as flat streams ----------------------------------------------------------------------
+// Without pooling y, dA, dY and the activation are the same contiguous (pixels x C) array, so the kernels walk it
+// as ONE stream of 16-byte vectors: thread t's vectors are t, t + stride, ... and, because C/8 divides the block
+// size and the stride, they all belong to the same channel octet (per-channel constants stay in registers).  The
+// row-structured versions had at most two loop iterations per image row (W*C/8 = 512 vectors per 256 threads) and
+// the load pipeline drained at every row change; here 4 independent iterations are always in flight.
+__global__ void __launch_bounds__(kRowThreads, 4)
+bn_relu_fwd_flat_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                        const float* __restrict__ shift, long long nvec, int C, __nv_bfloat16* __restrict__ out) {
+  const int CV = C >> 3, cv = threadIdx.x % CV;
+  float sc[8], sh[8];
+  load8f(scale + cv * 8, sc);
+  load8f(shift + cv * 8, sh);
+  const long long stride = (long long)gridDim.x * kRowThreads;
+#pragma unroll 4
+  for (long long v = (long long)blockIdx.x * kRowThreads + threadIdx.x; v < nvec; v += stride) {
+    float x[8], o[8];
+    unpack8(ldg16(y + v * 8), x);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = fmaxf(fmaf(x[k], sc[k], sh[k]), 0.f);
+    store8(out + v * 8, o);
+  }
+}
+
+template <bool kGradF32>
 __global__ void __launch_bounds__(kRowThreads, 3)
-bn_bwd_reduce_rows_kernel(const __nv_bfloat16* __restrict__ y, const void* __restrict__ dA_,
+bn_bwd_reduce_flat_kernel(const __nv_bfloat16* __restrict__ y, const void* __restrict__ dA_,
                           const float* __restrict__ scale, const float* __restrict__ shift,
-                          const float* __restrict__ mean, const float* __restrict__ invstd, int B, int H, int W,
-                          int C, float* __restrict__ partial) {
+                          const float* __restrict__ mean, const float* __restrict__ invstd, long long nvec, int C,
+                          float* __restrict__ partial) {
   extern __shared__ float s_red[];                 // [lanes][2*C]
-  const int CV = C >> 3, Ho = H / kPool, Wo = W / kPool;
-  const int cv = threadIdx.x % CV, pl = threadIdx.x / CV, lanes = kRowThreads / CV, cv_shift = __ffs(CV) - 1;
+  const int CV = C >> 3, cv = threadIdx.x % CV, pl = threadIdx.x / CV, lanes = kRowThreads / CV;
   float sc[8], sh[8], mu[8], is[8], sg[8], sgx[8];
   load8f(scale + cv * 8, sc);
   load8f(shift + cv * 8, sh);
@@ -318,32 +340,19 @@ bn_bwd_reduce_rows_kernel(const __nv_bfloat16* __restrict__ y, const void* __res
   load8f(invstd + cv * 8, is);
 #pragma unroll
   for (int k = 0; k < 8; ++k) sg[k] = sgx[k] = 0.f;
-  const int in_vecs = W * CV;
-  const int rows = B * H;
-  const float inv = kPool == 2 ? 0.25f : 1.0f;
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    const int b = row / H, h = row - b * H;
-    const int ho = h / kPool;
-    if (ho >= Ho) continue;                          // floor-mode tail row: no gradient
-    const __nv_bfloat16* yrow = y + (long long)row * W * C;
-    const long long drow = ((long long)b * Ho + ho) * Wo * C;
+  const long long stride = (long long)gridDim.x * kRowThreads;
 #pragma unroll 4
-    for (int v = threadIdx.x; v < in_vecs; v += kRowThreads) {
-      const int w = v >> cv_shift, wo = w / kPool;
-      if (wo >= Wo) continue;
-      const uint4 raw = ldg16(yrow + (long long)v * 8);
-      float g[8], x[8];
-      const long long o = drow + ((long long)wo * CV + cv) * 8;
-      if (kGradF32) load8f(reinterpret_cast<const float*>(dA_) + o, g);
-      else { const uint4 graw = ldg16(reinterpret_cast<const __nv_bfloat16*>(dA_) + o); unpack8(graw, g); }
-      unpack8(raw, x);
+  for (long long v = (long long)blockIdx.x * kRowThreads + threadIdx.x; v < nvec; v += stride) {
+    float g[8], x[8];
+    const uint4 raw = ldg16(y + v * 8);
+    if (kGradF32) load8f(reinterpret_cast<const float*>(dA_) + v * 8, g);
+    else unpack8(ldg16(reinterpret_cast<const __nv_bfloat16*>(dA_) + v * 8), g);
+    unpack8(raw, x);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float act = fmaf(x[k], sc[k], sh[k]);
-        const float gk = act > 0.f ? g[k] * inv : 0.f;
-        sg[k] += gk;
-        sgx[k] += gk * (x[k] - mu[k]) * is[k];
-      }
+    for (int k = 0; k < 8; ++k) {
+      const float gk = fmaf(x[k], sc[k], sh[k]) > 0.f ? g[k] : 0.f;
+      sg[k] += gk;
+      sgx[k] += gk * (x[k] - mu[k]) * is[k];
     }
   }
 #pragma unroll
@@ -359,67 +368,43 @@ bn_bwd_reduce_rows_kernel(const __nv_bfloat16* __restrict__ y, const void* __res
   }
 }
 
-// backward pass 2: dY = A*g + Bc*y + Cc for active elements (g = unpooled dA * 1/P^2 * relu mask)
-//   A = gamma*invstd, Bc = -A*mean(g*xhat)*invstd, Cc = -A*mean(g) - Bc*mean     (from coef, see finalize)
-template <int kPool, bool kGradF32>
+template <bool kGradF32>
 __global__ void __launch_bounds__(kRowThreads, 3)
-bn_bwd_apply_rows_kernel(const __nv_bfloat16* __restrict__ y, const void* __restrict__ dA_,
+bn_bwd_apply_flat_kernel(const __nv_bfloat16* __restrict__ y, const void* __restrict__ dA_,
                          const float* __restrict__ scale, const float* __restrict__ shift,
                          const float* __restrict__ mean, const float* __restrict__ invstd,
-                         const float* __restrict__ coef, int B, int H, int W, int C,
-                         __nv_bfloat16* __restrict__ dy) {
-  const int CV = C >> 3, Ho = H / kPool, Wo = W / kPool;
-  const int cv = threadIdx.x % CV, cv_shift = __ffs(CV) - 1;
+                         const float* __restrict__ coef, long long nvec, int C, __nv_bfloat16* __restrict__ dy) {
+  const int CV = C >> 3, cv = threadIdx.x % CV;
   float sc[8], sh[8], cA[8], cB[8], cC[8];
   {
-    float mu[8], is[8], c1[8], c2[8], c3[8];
+    float mu[8], is[8], c2[8], c3[8];
     load8f(scale + cv * 8, sc);
     load8f(shift + cv * 8, sh);
     load8f(mean + cv * 8, mu);
     load8f(invstd + cv * 8, is);
-    load8f(coef + cv * 8, c1);
+    load8f(coef + cv * 8, cA);
     load8f(coef + C + cv * 8, c2);
     load8f(coef + 2 * C + cv * 8, c3);
-    const float inv = kPool == 2 ? 0.25f : 1.0f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      cA[k] = c1[k] * inv;
-      cB[k] = -c1[k] * c3[k] * is[k];
-      cC[k] = -c1[k] * c2[k] - cB[k] * mu[k];
+      cB[k] = -cA[k] * c3[k] * is[k];
+      cC[k] = -cA[k] * c2[k] - cB[k] * mu[k];
     }
   }
-  const int in_vecs = W * CV;
-  const int rows = B * H;
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    const int b = row / H, h = row - b * H;
-    const int ho = h / kPool;
-    const bool row_in = ho < Ho;
-    const __nv_bfloat16* yrow = y + (long long)row * W * C;
-    __nv_bfloat16* orow = dy + (long long)row * W * C;
-    const long long drow = ((long long)b * Ho + (row_in ? ho : 0)) * Wo * C;
-#pragma unroll 2
-    for (int v = threadIdx.x; v < in_vecs; v += kRowThreads) {
-      const int w = v >> cv_shift, wo = w / kPool;
-      const bool inside = row_in && wo < Wo;
-      const uint4 raw = ldg16(yrow + (long long)v * 8);
-      float g[8], x[8], o[8];
-      if (inside) {
-        const long long oi = drow + ((long long)wo * CV + cv) * 8;
-        if (kGradF32) load8f(reinterpret_cast<const float*>(dA_) + oi, g);
-        else { const uint4 graw = ldg16(reinterpret_cast<const __nv_bfloat16*>(dA_) + oi); unpack8(graw, g); }
-      } else {
+  const long long stride = (long long)gridDim.x * kRowThreads;
+#pragma unroll 4
+  for (long long v = (long long)blockIdx.x * kRowThreads + threadIdx.x; v < nvec; v += stride) {
+    float g[8], x[8], o[8];
+    const uint4 raw = ldg16(y + v * 8);
+    if (kGradF32) load8f(reinterpret_cast<const float*>(dA_) + v * 8, g);
+    else unpack8(ldg16(reinterpret_cast<const __nv_bfloat16*>(dA_) + v * 8), g);
+    unpack8(raw, x);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) g[k] = 0.f;
-      }
-      unpack8(raw, x);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float act = fmaf(x[k], sc[k], sh[k]);
-        const float gk = act > 0.f ? g[k] : 0.f;
-        o[k] = fmaf(cA[k], gk, fmaf(cB[k], x[k], cC[k]));
-      }
-      store8(orow + (long long)v * 8, o);
+    for (int k = 0; k < 8; ++k) {
+      const float gk = fmaf(x[k], sc[k], sh[k]) > 0.f ? g[k] : 0.f;
+      o[k] = fmaf(cA[k], gk, fmaf(cB[k], x[k], cC[k]));
     }
+    store8(dy + v * 8, o);
   }
 }
 
@@ -623,9 +608,9 @@ int sed_bn_relu_pool_fwd(const void* y, const float* scale, const float* shift, 
   if (!out_is_f32 && rows_path_ok(H, W, C, ph, pw) && (long long)B * H < (1LL << 31)) {
     __nv_bfloat16* oo = reinterpret_cast<__nv_bfloat16*>(out);
     const int g = rows_grid(B * (H / ph), 4);
-    if (ph == 1) bn_relu_pool_fwd_rows_kernel<1><<<g, kRowThreads, 0, (cudaStream_t)stream>>>(yy, scale, shift, B, H, W, C, oo);
+    if (ph == 1) bn_relu_fwd_flat_kernel<<<sm_count() * 4, kRowThreads, 0, (cudaStream_t)stream>>>(yy, scale, shift, (long long)B * H * W * (C / 8), C, oo);
     else bn_relu_pool_fwd_rows_kernel<2><<<g, kRowThreads, 0, (cudaStream_t)stream>>>(yy, scale, shift, B, H, W, C, oo);
-    SED_LAUNCH_CHECK("bn_relu_pool_fwd_rows_kernel");
+    SED_LAUNCH_CHECK("bn_relu_pool_fwd_kernel (flat / rows)");
     return 0;
   }
   if (out_is_f32)
@@ -652,12 +637,14 @@ int sed_bn_relu_pool_bwd_reduce(const void* y, const void* dA, int grad_is_f32, 
   const __nv_bfloat16* yy = reinterpret_cast<const __nv_bfloat16*>(y);
   if (rows_path_ok(H, W, C, ph, pw) && (long long)B * H < (1LL << 31)) {
     cudaStream_t st = (cudaStream_t)stream;
-#define SED_RED(P, F) bn_bwd_reduce_rows_kernel<P, F><<<grid, kRowThreads, smem, st>>>(yy, dA, scale, shift, mean, invstd, B, H, W, C, partial)
-    if (ph == 1) { if (grad_is_f32) SED_RED(1, true); else SED_RED(1, false); }
+    const long long nvec = (long long)B * H * W * (C / 8);
+    if (ph == 1) {
+      if (grad_is_f32) bn_bwd_reduce_flat_kernel<true><<<grid, kRowThreads, smem, st>>>(yy, dA, scale, shift, mean, invstd, nvec, C, partial);
+      else bn_bwd_reduce_flat_kernel<false><<<grid, kRowThreads, smem, st>>>(yy, dA, scale, shift, mean, invstd, nvec, C, partial);
+    }
     else if (grad_is_f32) bn_bwd_reduce_win2_kernel<true><<<grid, kRowThreads, smem, st>>>(yy, dA, scale, shift, mean, invstd, B, H, W, C, partial);
     else bn_bwd_reduce_win2_kernel<false><<<grid, kRowThreads, smem, st>>>(yy, dA, scale, shift, mean, invstd, B, H, W, C, partial);
-#undef SED_RED
-    SED_LAUNCH_CHECK("bn_bwd_reduce_rows_kernel");
+    SED_LAUNCH_CHECK("bn_bwd_reduce_kernel");
     return 0;
   }
   if (grad_is_f32)
@@ -692,16 +679,18 @@ int sed_bn_relu_pool_bwd_apply(const void* y, const void* dA, int grad_is_f32, c
   __nv_bfloat16* dd = reinterpret_cast<__nv_bfloat16*>(dy);
   if (rows_path_ok(H, W, C, ph, pw) && (long long)B * H < (1LL << 31)) {
     cudaStream_t st = (cudaStream_t)stream;
-    const int g = rows_grid(B * H, 3);
-#define SED_APP(P, F) bn_bwd_apply_rows_kernel<P, F><<<g, kRowThreads, 0, st>>>(yy, dA, scale, shift, mean, invstd, coef, B, H, W, C, dd)
-    if (ph == 1) { if (grad_is_f32) SED_APP(1, true); else SED_APP(1, false); }
+    const long long nvec = (long long)B * H * W * (C / 8);
+    if (ph == 1) {
+      const int gf = sm_count() * 3;
+      if (grad_is_f32) bn_bwd_apply_flat_kernel<true><<<gf, kRowThreads, 0, st>>>(yy, dA, scale, shift, mean, invstd, coef, nvec, C, dd);
+      else bn_bwd_apply_flat_kernel<false><<<gf, kRowThreads, 0, st>>>(yy, dA, scale, shift, mean, invstd, coef, nvec, C, dd);
+    }
     else {
       const int g2 = rows_grid(B * (H / 2), 3);
       if (grad_is_f32) bn_bwd_apply_win2_kernel<true><<<g2, kRowThreads, 0, st>>>(yy, dA, scale, shift, mean, invstd, coef, B, H, W, C, dd);
       else bn_bwd_apply_win2_kernel<false><<<g2, kRowThreads, 0, st>>>(yy, dA, scale, shift, mean, invstd, coef, B, H, W, C, dd);
     }
-#undef SED_APP
-    SED_LAUNCH_CHECK("bn_bwd_apply_rows_kernel");
+    SED_LAUNCH_CHECK("bn_bwd_apply_kernel");
     return 0;
   }
   if (grad_is_f32)
