@@ -331,6 +331,30 @@ def run_ours(args):
                 'share_of_step': round(conv_ms / total_ms, 4),
                 'timing': 'CUDA events around every launch of three more steps on the compute stream'}
 
+    # ---- log-mel leg of the metric ("logmel Mframes/s"): the front-end kernel alone on this step's 512 resident clips
+    logmel = None
+    if rank == 0:
+        from sound_event_detection_dcase2017_task4_b200 import frontend as _fe
+        bank = model.logmel_extractor.mel_bank()
+        lm_out = torch.empty((b2, 1, CLIP_SAMPLES // 320 + 1, 64), device=dev)
+        for _ in range(3):
+            _fe.logmel(wave_dev, 320, bank, out=lm_out)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            _fe.logmel(wave_dev, 320, bank, out=lm_out)
+        e1.record()
+        torch.cuda.synchronize()
+        lm_ms = e0.elapsed_time(e1) / 10
+        frames = b2 * (CLIP_SAMPLES // 320 + 1)
+        lm_bytes = b2 * (CLIP_SAMPLES * 4 + (CLIP_SAMPLES // 320 + 1) * 64 * 4)
+        logmel = {'mframes_per_s': round(frames / lm_ms / 1e3, 1), 'ms': round(lm_ms, 4),
+                  'clips': b2, 'achieved_gbs': round(lm_bytes / lm_ms / 1e6, 1), 'hbm_peak_gbs': measured_peaks()['hbm_gbs'],
+                  'hbm_frac': round(lm_bytes / lm_ms / 1e6 / measured_peaks()['hbm_gbs'], 4),
+                  'bytes_per_clip': lm_bytes // b2,
+                  'note': 'fp32 in + fp32 log-mel out (SURVEY 8d); the kernel is shared-memory-bandwidth bound, not HBM bound'}
+
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -370,6 +394,7 @@ def run_ours(args):
             'gpu_launches': launches,
             'clocks': clock_info,
             'roofline': roof,
+            'logmel': logmel,
             'cpu_baseline': cpu,
             'kernel_shares': shares,
         }
