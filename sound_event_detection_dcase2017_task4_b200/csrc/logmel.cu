@@ -63,6 +63,12 @@ __device__ __forceinline__ void dft8(float2 (&v)[8]) {
   dft4(b0, b1, b2, b3, v[1], v[3], v[5], v[7]);
 }
 
+// the 64 threads (2 warps) of one frame slot only exchange data among themselves: a named barrier per slot lets the
+// four slots of a CTA drift apart instead of meeting at a CTA-wide barrier five times per frame
+__device__ __forceinline__ void slot_barrier(int slot) {
+  asm volatile("bar.sync %0, 64;" ::"r"(slot + 1) : "memory");
+}
+
 __device__ __forceinline__ int zaddr(int k) { return k + 4 * (k >> 5); }   // padded Z layout (<576)
 
 template <typename T> struct Sample;
@@ -90,9 +96,7 @@ __global__ void __launch_bounds__(kThreads, 3)
 logmel_kernel(const InT* __restrict__ wave, int n_clips, int n_samples, int hop, int n_frames,
               int chunks_per_clip, MelBank mel, float* __restrict__ out) {
   extern __shared__ __align__(16) float smem[];
-  float* s_win = smem;                       // [1024] periodic Hann
-  float* s_tw = s_win + kNfft;               // [512][2] W1024^k for the even/odd split
-  float* s_work = s_tw + kNfft;              // [kSlots][4][kBuf]  A.re A.im B.re B.im
+  float* s_work = smem;                      // [kSlots][4][kBuf]  A.re A.im B.re B.im
   float* s_span = s_work + kSlots * 4 * kBuf;  // [(FPC-1)*hop + 1024]
 
   const int tid = threadIdx.x;
@@ -103,23 +107,25 @@ logmel_kernel(const InT* __restrict__ wave, int n_clips, int n_samples, int hop,
   float* B_re = A_im + kBuf;
   float* B_im = B_re + kBuf;
 
-  // ---- prologue: window, split twiddles, per-thread stage twiddles -------------------------
-  for (int n = tid; n < kNfft; n += kThreads) s_win[n] = 0.5f - 0.5f * cospif(2.0f * (float)n / (float)kNfft);
-  for (int k = tid; k < kHalf; k += kThreads) {
-    float2 t = twiddle(k, kNfft);
-    s_tw[2 * k] = t.x;
-    s_tw[2 * k + 1] = t.y;
-  }
+  // ---- prologue: everything a thread needs for every frame lives in its registers -----------
+  // (the window samples and split twiddles used to be re-read from shared memory for every frame: the kernel is
+  //  shared-memory-bandwidth bound, so they are per-thread constants now)
   float2 tw1[8], tw2[8];                      // W512^(j q)  and  W64^(j0 p)
+  float2 win[8];                              // periodic Hann at samples 2(j + 64 r), 2(j + 64 r) + 1
+  float2 tws[4];                              // W1024^(j + 64 s), s = 0..3, for the even/odd split
   {
     const int j0 = j & 7;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       tw1[q] = twiddle((j * q) & 511, 512);
       tw2[q] = twiddle((j0 * q) & 63, 64);
+      const int n2 = 2 * (j + 64 * q);
+      win[q] = make_float2(0.5f - 0.5f * cospif(2.0f * (float)n2 / (float)kNfft),
+                           0.5f - 0.5f * cospif(2.0f * (float)(n2 + 1) / (float)kNfft));
     }
+#pragma unroll
+    for (int sI = 0; sI < 4; ++sI) tws[sI] = twiddle(j + 64 * sI, kNfft);
   }
-  __syncthreads();
 
   const long long total_items = (long long)n_clips * chunks_per_clip;
   for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -170,8 +176,7 @@ logmel_kernel(const InT* __restrict__ wave, int n_clips, int n_samples, int hop,
         for (int r = 0; r < 8; ++r) {
           const int n2 = 2 * (j + 64 * r);             // 8-byte aligned: hop and n2 are even
           const float2 xs = *reinterpret_cast<const float2*>(x + n2);
-          const float2 ws = *reinterpret_cast<const float2*>(s_win + n2);
-          v[r] = make_float2(xs.x * ws.x, xs.y * ws.y);
+          v[r] = make_float2(xs.x * win[r].x, xs.y * win[r].y);
         }
         dft8(v);
 #pragma unroll
@@ -181,7 +186,7 @@ logmel_kernel(const InT* __restrict__ wave, int n_clips, int n_samples, int hop,
           A_im[q * 72 + j] = y.y;
         }
       }
-      __syncthreads();
+      slot_barrier(slot);
       // ---- pass 2: thread (q, j0): DFT8 over j1 of A[q][j0 + 8 j1], twiddle W64^(j0 p) -> B --
       if (live) {
         const int q = j >> 3, j0 = j & 7;
@@ -195,7 +200,7 @@ logmel_kernel(const InT* __restrict__ wave, int n_clips, int n_samples, int hop,
           B_im[q * 72 + j0 * 9 + p] = u.y;
         }
       }
-      __syncthreads();
+      slot_barrier(slot);
       // ---- pass 3: thread (q, p): DFT8 over j0 -> Z[q + 8 p + 64 s] -> A (padded linear) -----
       if (live) {
         const int q = j >> 3, p = j & 7;
@@ -209,29 +214,32 @@ logmel_kernel(const InT* __restrict__ wave, int n_clips, int n_samples, int hop,
           A_im[zaddr(k)] = v[s].y;
         }
       }
-      __syncthreads();
+      slot_barrier(slot);
       // ---- even/odd split -> power spectrum P[0..512] -> B_re ---------------------------------
       float* P = B_re;                              // 513 <= kBuf
+      // Bins k and 512-k share their inputs: with E = (Z[k] + conj Z[512-k])/2, O = (Z[k] - conj Z[512-k])/(2i) and
+      // t = W1024^k O,  X[k] = E + t  and  X[512-k] = conj(E - t).  Thread j takes k = j + 64 s, s = 0..3 (and their
+      // partners 512-k; k = 0 pairs with the Nyquist bin), thread 0 also the self-paired k = 256.
       if (live) {
 #pragma unroll
-        for (int s = 0; s < 8; ++s) {
-          const int k = j + 64 * s;
+        for (int sI = 0; sI < 4; ++sI) {
+          const int k = j + 64 * sI;
           const int km = (kHalf - k) & (kHalf - 1);
           const float2 zk = make_float2(A_re[zaddr(k)], A_im[zaddr(k)]);
           const float2 zm = make_float2(A_re[zaddr(km)], -A_im[zaddr(km)]);   // conj Z[512-k]
           const float2 e = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y + zm.y));
           const float2 d = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y - zm.y));
-          const float2 o = mul_neg_i(d);            // (Zk - conj Zm) / (2i)
-          const float2 w = make_float2(s_tw[2 * k], s_tw[2 * k + 1]);
-          const float2 xk = cadd(e, cmul(w, o));
-          P[k] = xk.x * xk.x + xk.y * xk.y;
-          if (k == 0) {                             // Nyquist bin: X[512] = E[0] - O[0]
-            const float2 xn = csub(e, o);
-            P[kHalf] = xn.x * xn.x + xn.y * xn.y;
-          }
+          const float2 t = cmul(tws[sI], mul_neg_i(d));                       // W^k (Zk - conj Zm) / (2i)
+          const float2 xp = cadd(e, t), xm = csub(e, t);
+          P[k] = xp.x * xp.x + xp.y * xp.y;
+          P[kHalf - k] = xm.x * xm.x + xm.y * xm.y;
+        }
+        if (j == 0) {                               // k = 256: Z[256] pairs with itself, W1024^256 = -i
+          const float2 z = make_float2(A_re[zaddr(256)], A_im[zaddr(256)]);
+          P[256] = z.x * z.x + z.y * z.y;           // |Re z - i Im z|^2
         }
       }
-      __syncthreads();
+      slot_barrier(slot);
       if (live) {
         const long long frame = (long long)clip * n_frames + frame0 + f;
         if (kPower) {
@@ -263,7 +271,7 @@ int launch_logmel(const InT* wave, int n_clips, int n_samples, int hop, MelBank 
   SED_REQUIRE(wave && out, "%s: null pointer", name);
   const int n_frames = n_samples / hop + 1;
   const int chunks = ceil_div(n_frames, kFramesPerChunk);
-  const size_t smem = sizeof(float) * (size_t)(2 * kNfft + kSlots * 4 * kBuf + (kFramesPerChunk - 1) * hop + kNfft);
+  const size_t smem = sizeof(float) * (size_t)(kSlots * 4 * kBuf + (kFramesPerChunk - 1) * hop + kNfft);
   auto kern = logmel_kernel<InT, kPower>;
   static thread_local int configured_dev = -1;   // attribute is per (function, device)
   int dev = 0;
