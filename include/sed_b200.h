@@ -75,10 +75,10 @@ int sed_mel_db_f32(const float* power, long long rows, int n_bins,
 /* fp32 OIHW master weights -> bf16 shadows: fwd [Cout][tap][Cin]; dgrad [Cin][8-tap][Cout]. */
 int sed_conv_pack_weights(const float* w_oihw, int Cout, int Cin, void* fwd_pack, void* dgrad_pack,
                           sed_stream_t stream);
-/* grid size the conv kernel will use = number of rows of the stats_partial workspace. */
+/* number of rows of the stats_partial workspace (4 per CTA of the persistent grid: one per TMEM lane quarter). */
 int sed_conv3x3_tc_grid(int B, int H, int W, int Cin, int Cout);
 /* y = conv3x3(x, w) (bf16 out, fp32 accumulate).  stats_partial (optional):
- * [sed_conv3x3_tc_grid()][2][Cout] per-CTA (sum, sum of squares) of the fp32 results, for the
+ * [sed_conv3x3_tc_grid()][2][Cout] partial (sum, sum of squares) rows of the fp32 results, for the
  * training-mode BatchNorm that follows.  The data gradient is the same call with
  * x = dY, wpack = the dgrad pack and Cin/Cout swapped. */
 int sed_conv3x3_tc_fwd(const void* x, const void* wpack, void* y, float* stats_partial, int B, int H,

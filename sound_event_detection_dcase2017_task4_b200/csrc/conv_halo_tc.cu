@@ -70,7 +70,7 @@ struct HaloParams {
   int a_bytes;         // (rows_per_tile + 2) * W * 128
   int a_stages, b_stages;
   __nv_bfloat16* y;    // NHWC output
-  float* stats;        // [gridDim.x][2][Cout] partial (sum, sumsq) or nullptr
+  float* stats;        // [gridDim.x * 4][2][Cout] partial (sum, sumsq) rows, one per (CTA, TMEM lane quarter), or nullptr
   // fused first pass of the BatchNorm+ReLU(+2x2 avg-pool) backward of the layer BELOW (kBnr kernels, data gradient):
   // this kernel's output is that layer's dA; partials of sum(g) and sum(g*y), g = unpool(dA)/pool^2 * [bn(y) > 0]
   const __nv_bfloat16* bnr_y;      // raw conv output of the layer below: [B][H*pool (+tail)][W*pool][Cout]
@@ -99,12 +99,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __shared__ uint64_t a_full[kMaxAStages], a_empty[kMaxAStages], b_full[kMaxBStages], b_empty[kMaxBStages];
   __shared__ uint64_t tmem_full_bar[2], tmem_empty_bar[2], b_res_full;
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float s_stats[2 * 512];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  for (int i = threadIdx.x; i < 2 * p.Cout; i += kHThreads) s_stats[i] = 0.f;
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
@@ -222,6 +220,19 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // epilogue is on the critical path) over ALL tiles of the CTA -- before the 32x32 warp transpose-reduce runs.
     constexpr bool kLocalStats = kN == 64;
     constexpr int kChunksPerWarp = kN / 64;
+    // Each (CTA, lane quarter) owns one partial row in global memory and each of its two warps owns every other
+    // 32-channel chunk of it, so the running sums are plain read-modify-writes by their only writer: no atomics, and
+    // the finalize kernel adds the rows in a fixed order -- bit-reproducible statistics.
+    float* stat_row = p.stats == nullptr ? nullptr : p.stats + ((long long)blockIdx.x * 4 + q) * 2 * p.Cout;
+    if (stat_row != nullptr && !kLocalStats) {
+      for (int nt = 0; nt < p.tiles_n; ++nt)
+#pragma unroll
+        for (int j = 0; j < kChunksPerWarp; ++j) {
+          const int ch = nt * kN + (half + 2 * j) * 32 + lane;
+          stat_row[ch] = 0.f;
+          stat_row[p.Cout + ch] = 0.f;
+        }
+    }
     float s_acc[32], ss_acc[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) s_acc[i] = ss_acc[i] = 0.f;
@@ -297,8 +308,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (!kLocalStats && p.stats != nullptr) {
           warp_transpose_reduce2(s_acc, ss_acc, lane);
           const int ch = n_tile * kN + c * 32 + lane;
-          atomicAdd(&s_stats[ch], s_acc[0]);
-          atomicAdd(&s_stats[p.Cout + ch], ss_acc[0]);
+          stat_row[ch] += s_acc[0];
+          stat_row[p.Cout + ch] += ss_acc[0];
 #pragma unroll
           for (int i = 0; i < 32; ++i) s_acc[i] = ss_acc[i] = 0.f;
         }
@@ -306,15 +317,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       tcgen05_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);
     }
-    if (p.stats != nullptr) {
-      if (kLocalStats) {                               // kN == 64: Cout == 64, a single n tile
-        warp_transpose_reduce2(s_acc, ss_acc, lane);
-        atomicAdd(&s_stats[half * 32 + lane], s_acc[0]);
-        atomicAdd(&s_stats[p.Cout + half * 32 + lane], ss_acc[0]);
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(kHEpiThreads) : "memory");
-      float* out = p.stats + (long long)blockIdx.x * 2 * p.Cout;
-      for (int i = threadIdx.x - 64; i < 2 * p.Cout; i += kHEpiThreads) out[i] = s_stats[i];
+    if (kLocalStats && stat_row != nullptr) {          // kN == 64: Cout == 64, a single n tile; one reduce per warp
+      warp_transpose_reduce2(s_acc, ss_acc, lane);
+      stat_row[half * 32 + lane] = s_acc[0];
+      stat_row[p.Cout + half * 32 + lane] = ss_acc[0];
     }
   }
   tcgen05_fence_before();
@@ -378,10 +384,10 @@ using namespace sed;
 
 extern "C" {
 
-int sed_conv3x3_tc_grid(int B, int H, int W, int Cin, int Cout) {
+int sed_conv3x3_tc_grid(int B, int H, int W, int Cin, int Cout) {   // rows of the statistics workspace: 4 per CTA
   HaloPlan q;
   if (!make_plan(B, H, W, Cin, Cout, &q)) return 0;
-  return q.grid;
+  return q.grid * 4;
 }
 
 static int conv_halo_dispatch(const void* x, const void* wpack, void* y, float* stats_partial, int B, int H, int W,

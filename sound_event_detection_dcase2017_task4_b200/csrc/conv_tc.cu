@@ -1,27 +1,12 @@
-// conv_tc.cu -- 3x3 / stride 1 / pad 1 convolution as a tcgen05 implicit GEMM (sm_100a).
+// conv_tc.cu -- plain tensor-core GEMM on the one-box-per-K-block tcgen05 pipeline (sm_100a):
+//   out[M][N] = A[M][K] * Bw[N][K]^T (+ bias),  A / Bw bf16 K-major, out fp32.
+// Used for the GRU / attention projections (x @ W^T) of /root/reference/pytorch/models.py:475/:566 (nn.GRU input
+// projection) and :641-665 (MultiHead), optionally with the 3-way bf16 operand split (sed_split_bf16x3) for
+// fp32-class accuracy.  (The 3x3 convolutions moved to the halo-tile kernel in conv_halo_tc.cu.)
 //
-// Replaces the cuDNN calls behind ConvBlock.conv1/conv2 (/root/reference/pytorch/models.py:75-83,
-// forward :102-103) for every layer with Cin % 64 == 0, and -- with the rotated / transposed
-// weight pack -- their data-gradient.
-//
-//   D[M = 128 pixels][N = Cout tile] = sum over 9 taps x (Cin/64) K-blocks  A_tap[128][64] * W_tap[N][64]^T
-//
-// * activations are NHWC bf16; an M tile is a (bh x W) rectangle of output pixels of one clip,
-//   bh*W = 128.  For tap (kh,kw) the A operand is the same rectangle shifted by (kh-1, kw-1):
-//   ONE 4-D TMA box {64 ch, W, bh, 1} at coordinates {c0, kw-1, h0+kh-1, b}.  Out-of-range
-//   coordinates are zero-filled by the TMA unit, which IS the conv's zero padding (and the H
-//   tail), so the im2col matrix never exists anywhere -- not in HBM, not in shared memory.
-// * weights are a bf16 [Cout][9*Cin] K-major matrix (k = tap*Cin + ci): 2-D TMA box {64, N}.
-// * both land in 128B-swizzled K-major shared-memory tiles that tcgen05.mma consumes directly;
-//   fp32 accumulators live in TMEM (double buffered: the epilogue of tile i overlaps the MMAs
-//   of tile i+1).
-// * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2-9 = epilogue
-//   (two warps per TMEM lane quarter, each taking every other 32-column chunk -- the K = 576 layers
-//   are epilogue-bound with one warp per quarter):
-//   tcgen05.ld -> bf16 NHWC store, and per-channel sum / sum-of-squares of the fp32
-//   accumulators for the training-mode BatchNorm that follows (warp-transpose reduction,
-//   accumulated per CTA in shared memory, flushed once: deterministic two-level reduction).
-// * persistent: grid = min(#tiles, #SMs), static round-robin tile schedule.
+// warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2-9 = epilogue; 128B-swizzled K-major tiles
+// consumed directly by tcgen05.mma.kind::f16 (M = 128, N tile <= 256, K = 16), fp32 accumulators double buffered in
+// TMEM, persistent static round-robin tile schedule.
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -69,13 +54,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t full_bar[C::kStages], empty_bar[C::kStages], tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float s_stats[2 * 512];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_kb = kGemm ? p.gemm_kb : 9 * p.kb_per_tap;
+  const int num_kb = p.gemm_kb;
 
-  for (int i = threadIdx.x; i < 2 * p.Cout; i += kNumThreads) s_stats[i] = 0.f;
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
@@ -103,9 +86,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int n_tile = tile % p.tiles_n;
         const int m_tile = tile / p.tiles_n;
-        const int b = m_tile / p.tiles_h;
-        const int h0 = (m_tile % p.tiles_h) * p.bh;
-        if (kGemm) {
+        {
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * C::kStageBytes;
@@ -113,19 +94,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
             tma_load_4d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m_tile * kBlockM, 0, 0);
             tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kBlockK, n_tile * kN);
-            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
-          }
-          continue;
-        }
-        for (int tap = 0; tap < 9; ++tap) {
-          const int kh = tap / 3, kw = tap % 3;
-          for (int cb = 0; cb < p.kb_per_tap; ++cb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem + stage * C::kStageBytes;
-            uint8_t* sb = sa + kABytes;
-            mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
-            tma_load_4d(sa, &tmap_a, &full_bar[stage], cb * kBlockK, kw - 1, h0 + kh - 1, b);
-            tma_load_2d(sb, &tmap_b, &full_bar[stage], tap * p.Cin + cb * kBlockK, n_tile * kN);
             if (++stage == C::kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -166,19 +134,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;              // which of the two warps of this quarter
     const int row = q * 32 + lane;
-    const int r_h = row / p.W, r_w = row % p.W;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int n_tile = tile % p.tiles_n;
       const int m_tile = tile / p.tiles_n;
-      const int b = m_tile / p.tiles_h;
-      const int h = (m_tile % p.tiles_h) * p.bh + r_h;
-      const bool valid = h < p.H;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
-      if (kGemm) {
+      {
         const long long m = (long long)m_tile * kBlockM + row;
         const bool ok = m < p.gemm_m;
         float* drow = p.out_f32 + m * p.Cout + n_tile * kN;
@@ -198,58 +162,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         }
         tcgen05_fence_before();
         mbar_arrive(&tmem_empty_bar[acc]);
-        continue;
       }
-      __nv_bfloat16* dst = p.y + (((long long)b * p.H + h) * p.W + r_w) * p.Cout + n_tile * kN;
-#pragma unroll 1
-      for (int c = half; c < kN / 32; c += 2) {
-        float v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kN + c * 32, v);
-        if (valid) {
-          uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 o;
-            o.x = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]);
-            o.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
-            o.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
-            o.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
-            d4[g] = o;
-          }
-        }
-        if (p.stats != nullptr) {
-          float sq[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            v[i] = valid ? v[i] : 0.f;
-            sq[i] = v[i] * v[i];
-          }
-          // warp transpose-reduce: afterwards lane l holds the column-(l) total over the 32 rows
-#pragma unroll
-          for (int off = 16; off >= 1; off >>= 1) {
-            const bool hi = (lane & off) != 0;
-#pragma unroll
-            for (int i = 0; i < off; ++i) {
-              const float send = hi ? v[i] : v[i + off];
-              const float keep = hi ? v[i + off] : v[i];
-              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-              const float send2 = hi ? sq[i] : sq[i + off];
-              const float keep2 = hi ? sq[i + off] : sq[i];
-              sq[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
-            }
-          }
-          const int ch = n_tile * kN + c * 32 + lane;
-          atomicAdd(&s_stats[ch], v[0]);
-          atomicAdd(&s_stats[p.Cout + ch], sq[0]);
-        }
-      }
-      tcgen05_fence_before();
-      mbar_arrive(&tmem_empty_bar[acc]);
-    }
-    if (p.stats != nullptr) {
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-      float* out = p.stats + (long long)blockIdx.x * 2 * p.Cout;
-      for (int i = threadIdx.x - 64; i < 2 * p.Cout; i += kEpiThreads) out[i] = s_stats[i];
     }
   }
   tcgen05_fence_before();
