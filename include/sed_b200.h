@@ -194,7 +194,7 @@ int sed_colsum_f32(const float* x, long long rows, int C, float* partial, sed_st
 /* ---- bidirectional GRU recurrence: nn.GRU(512, 256, bidirectional) (pytorch/models.py:437-438,
  * :529-530; calls :475, :566).  gx = x W_ih^T + b_ih for both directions (B,T,2,3H), gate order
  * r,z,n; w_hh (2,3H,H), b_hh (2,3H); out (B,T,2H); gates (B,T,2,4,H) saved for the backward.
- * sync_ws: >= 8 * ceil(B/32) bytes of scratch for the persistent kernel's group counters (H = 256; the
+ * sync_ws: >= 16 * ceil(B/32) bytes of scratch for the persistent kernel's group counters (H = 256; the
  * entry point zeroes it on the stream); NULL selects the per-step kernels.
  * bwd: carry = (2,2,B,H) scratch; writes dgx, dgh (B,T,2,3H) and hprev (B,T,2,H). */
 int sed_gru_fwd(const float* gx, const float* w_hh, const float* b_hh, float* out, float* gates, void* sync_ws,

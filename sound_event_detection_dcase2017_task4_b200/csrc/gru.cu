@@ -164,12 +164,18 @@ constexpr int kPJ = 32;            // hidden units per CTA
 constexpr int kPGroup = kPH / kPJ; // 8 CTAs per group
 constexpr int kPThreads = 256;
 
-// All CTAs of a group arrive; everyone leaves once `target` arrivals have been counted.  Writes made by any
-// thread of the CTA before the call are visible to every thread of the group after it (bar.sync, then
-// thread 0: fence + atomic + acquire spin, then bar.sync -- the cooperative-groups grid.sync pattern).
-__device__ __forceinline__ void group_barrier(unsigned int* ctr, unsigned int target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
+// Group barrier for one 16-row half of a CTA (4 warps, named barrier `bar_id`): all 8 CTAs of the group arrive on the
+// half's counter; everyone leaves once `target` arrivals have been counted.  Writes made by any thread of the half
+// before the call are visible to every thread of the group's halves after it (bar.sync, then the leader thread:
+// fence + atomic + acquire spin, then bar.sync -- the cooperative-groups grid.sync pattern).  The two halves of a
+// CTA own disjoint batch rows, i.e. independent recurrences, and use separate counters: while one half waits for its
+// barrier the other one computes, which hides most of the per-step exchange latency.
+__device__ __forceinline__ void half_barrier_sync(int bar_id) {
+  asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+}
+__device__ __forceinline__ void group_barrier_half(unsigned int* ctr, unsigned int target, int bar_id, bool leader) {
+  half_barrier_sync(bar_id);
+  if (leader) {
     __threadfence();
     atomicAdd(ctr, 1u);
     unsigned int v;
@@ -179,11 +185,11 @@ __device__ __forceinline__ void group_barrier(unsigned int* ctr, unsigned int ta
       if (++spins > (1u << 28)) { printf("sed: GRU group barrier timed out\n"); __trap(); }
     } while (v < target);
   }
-  __syncthreads();
+  half_barrier_sync(bar_id);
 }
 
 struct GruPersist {
-  unsigned int* sync_ctr;   // [tiles][2] arrive counters (zeroed by the host entry point)
+  unsigned int* sync_ctr;   // [tiles][2 directions][2 halves] arrive counters (zeroed by the host entry point)
   int B, T, b_base;
 };
 
@@ -219,6 +225,38 @@ __device__ __forceinline__ void stage_split(const float* __restrict__ src, long 
     *reinterpret_cast<uint2*>(s_lo + r * ld + c4 * 4) = make_uint2(l0, l1);
   }
 }
+// The per-step exchange tile (16 rows of the group's h / dGh, read through L2): compile-time shape so that a thread
+// issues its loads in batches of 8 independent 16-byte requests before converting any of them -- one L2 round trip
+// per batch instead of one per element (this staging, not the matrix product, was the per-step critical path).
+template <int kRows, int kCols, int kThreadsN>
+__device__ __forceinline__ void stage_split_tile(const float* __restrict__ src, long long src_stride, bool have,
+                                                 int valid_rows, __nv_bfloat16* __restrict__ s_hi,
+                                                 __nv_bfloat16* __restrict__ s_lo, int ld, int tid) {
+  constexpr int kC4 = kCols / 4;
+  constexpr int kPer = kRows * kC4 / kThreadsN;
+  static_assert(kRows * kC4 % kThreadsN == 0 && kPer % 8 == 0, "tile must split into batches of 8 per thread");
+#pragma unroll
+  for (int base = 0; base < kPer; base += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = (base + u) * kThreadsN + tid;
+      const int r = i / kC4, c4 = i - r * kC4;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (have && r < valid_rows) v[u] = __ldcg(reinterpret_cast<const float4*>(src + r * src_stride + c4 * 4));
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = (base + u) * kThreadsN + tid;
+      const int r = i / kC4, c4 = i - r * kC4;
+      uint32_t h0, l0, h1, l1;
+      split2(v[u].x, v[u].y, h0, l0);
+      split2(v[u].z, v[u].w, h1, l1);
+      *reinterpret_cast<uint2*>(s_hi + r * ld + c4 * 4) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(s_lo + r * ld + c4 * 4) = make_uint2(l0, l1);
+    }
+  }
+}
 constexpr int kLdK = kPH + 8;          // bf16 row stride of the K = 256 tiles (528 B: conflict-free fragment loads)
 constexpr int kLdG = 3 * kPH + 8;      // bf16 row stride of the K = 768 tiles
 
@@ -237,14 +275,16 @@ gru_fwd_persistent_kernel(const float* __restrict__ Gx, const float* __restrict_
   constexpr int H = kPH;
   const int B = q.B, T = q.T;
   const int j0 = blockIdx.x * kPJ, b0 = q.b_base + blockIdx.y * kPB, d = blockIdx.z;
-  unsigned int* ctr = q.sync_ctr + (blockIdx.y * 2 + d);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int gid = lane >> 2, tig = lane & 3;
   const float* W = Whh + (long long)d * 3 * H * H;
   for (int g = 0; g < 3; ++g)          // rows g*32 .. g*32+31 of the slice = W_hh rows g*H + j0 ..
     stage_split(W + ((long long)g * H + j0) * H, H, kPJ, H, true, kPJ, sWh + g * kPJ * kLdK, sWl + g * kPJ * kLdK, kLdK,
                 tid, kPThreads);
-  const int mt = warp & 1, oct = warp >> 1;
+  const int mt = warp & 1, oct = warp >> 1;                             // half (16 batch rows) / unit octet
+  const int ht = oct * 32 + lane;                                       // thread index within the half (0..127)
+  unsigned int* ctr = q.sync_ctr + ((blockIdx.y * 2 + d) * 2 + mt);
+  __syncthreads();                                                      // the W_hh slice is staged
   const int row0 = mt * 16 + gid;                                       // this thread's rows: row0, row0 + 8
   const int jl = oct * 8 + tig * 2;                                     // its units: j0 + jl, j0 + jl + 1
   const int j = j0 + jl;
@@ -269,11 +309,12 @@ gru_fwd_persistent_kernel(const float* __restrict__ Gx, const float* __restrict_
         for (int g = 0; g < 3; ++g) gx[rr][g] = __ldg(reinterpret_cast<const float2*>(gp + g * H));
       }
     }
-    if (s > 0) group_barrier(ctr, (unsigned int)(kPGroup * s));         // h_{t-1} of all 8 CTAs is in L2
-    else __syncthreads();
-    stage_split(out + ((long long)b0 * T + tp) * 2 * H + d * H, (long long)T * 2 * H, kPB, H, s > 0, B - b0, sHh, sHl,
-                kLdK, tid, kPThreads);
-    __syncthreads();
+    // h_{t-1} of this half's 16 rows, produced by all 8 CTAs of the group, is in L2
+    if (s > 0) group_barrier_half(ctr, (unsigned int)(kPGroup * s), 1 + mt, ht == 0);
+    else half_barrier_sync(1 + mt);
+    stage_split_tile<16, kPH, 128>(out + ((long long)(b0 + mt * 16) * T + tp) * 2 * H + d * H, (long long)T * 2 * H,
+                                   s > 0, B - b0 - mt * 16, sHh + mt * 16 * kLdK, sHl + mt * 16 * kLdK, kLdK, ht);
+    half_barrier_sync(1 + mt);
     float acc[3][4];
 #pragma unroll
     for (int g = 0; g < 3; ++g)
@@ -333,7 +374,7 @@ gru_fwd_persistent_kernel(const float* __restrict__ Gx, const float* __restrict_
       }
     }
     // (the next iteration's barrier orders these stores before any other CTA's read, and its leading
-    //  __syncthreads orders this step's shared-memory reads before the refill)
+    //  half-barrier orders this step's shared-memory reads before the refill)
   }
 }
 
@@ -354,7 +395,6 @@ gru_bwd_persistent_kernel(const float* __restrict__ dout, const float* __restric
   constexpr int H = kPH;
   const int B = q.B, T = q.T;
   const int k0 = blockIdx.x * kPJ, b0 = q.b_base + blockIdx.y * kPB, d = blockIdx.z;
-  unsigned int* ctr = q.sync_ctr + (blockIdx.y * 2 + d);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int gid = lane >> 2, tig = lane & 3;
   const float* W = Whh + (long long)d * 3 * H * H;
@@ -366,6 +406,9 @@ gru_bwd_persistent_kernel(const float* __restrict__ dout, const float* __restric
     sWl[kl * kLdG + row] = __float2bfloat16_rn(v - hi);
   }
   const int mt = warp & 1, oct = warp >> 1;
+  const int ht = oct * 32 + lane;                                       // thread index within the 16-row half
+  unsigned int* ctr = q.sync_ctr + ((blockIdx.y * 2 + d) * 2 + mt);
+  __syncthreads();                                                      // the transposed W_hh slice is staged
   const int row0 = mt * 16 + gid;
   const int j = k0 + oct * 8 + tig * 2;                                 // this thread's units: j, j + 1
   float carry[2][2] = {{0.f, 0.f}, {0.f, 0.f}};                         // dh flowing back from the later time step
@@ -410,10 +453,12 @@ gru_bwd_persistent_kernel(const float* __restrict__ dout, const float* __restric
       }
     }
     if (bs == T - 1) break;                              // dh of the step before the first is not needed
-    group_barrier(ctr, (unsigned int)(kPGroup * (bs + 1)));   // every CTA's dGh slice of this step is in L2
-    stage_split(dGh + (((long long)b0 * T + tt) * 2 + d) * 3 * H, (long long)T * 2 * 3 * H, kPB, 3 * H, true, B - b0,
-                sDh, sDl, kLdG, tid, kPThreads);
-    __syncthreads();
+    // every CTA's dGh slice of this step (this half's 16 rows) is in L2
+    group_barrier_half(ctr, (unsigned int)(kPGroup * (bs + 1)), 1 + mt, ht == 0);
+    stage_split_tile<16, 3 * kPH, 128>(dGh + (((long long)(b0 + mt * 16) * T + tt) * 2 + d) * 3 * H,
+                                       (long long)T * 2 * 3 * H, true, B - b0 - mt * 16, sDh + mt * 16 * kLdG,
+                                       sDl + mt * 16 * kLdG, kLdG, ht);
+    half_barrier_sync(1 + mt);
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     const __nv_bfloat16* ah = sDh + row0 * kLdG + tig * 2;
     const __nv_bfloat16* al = sDl + row0 * kLdG + tig * 2;
@@ -442,7 +487,7 @@ gru_bwd_persistent_kernel(const float* __restrict__ dout, const float* __restric
     for (int rr = 0; rr < 2; ++rr)
 #pragma unroll
       for (int u = 0; u < 2; ++u) carry[rr][u] = acc[rr * 2 + u] + dhz[rr][u];
-    // (the next barrier's leading __syncthreads orders these shared-memory reads before the refill)
+    // (the next barrier's leading half-barrier orders these shared-memory reads before the refill)
   }
 }
 
@@ -457,10 +502,10 @@ int launch_gru_persistent(const void* kern, const char* name, size_t smem, int B
   const int max_tiles = per_sm * sm_count() / (kPGroup * 2);
   SED_REQUIRE(max_tiles >= 1, "%s: the device cannot hold one batch tile", name);
   const int tiles = (B + kPB - 1) / kPB;
-  SED_CUDA(cudaMemsetAsync(sync_ws, 0, sizeof(unsigned int) * 2 * (size_t)tiles, stream));
+  SED_CUDA(cudaMemsetAsync(sync_ws, 0, sizeof(unsigned int) * 4 * (size_t)tiles, stream));
   for (int t0 = 0; t0 < tiles; t0 += max_tiles) {
     const int nt = tiles - t0 < max_tiles ? tiles - t0 : max_tiles;
-    GruPersist q{sync_ws + 2 * t0, B, T, t0 * kPB};
+    GruPersist q{sync_ws + 4 * t0, B, T, t0 * kPB};
     void* args[12];
     const int n = fill_args(args);
     args[n] = &q;

@@ -35,7 +35,7 @@ def gru_forward(gru, feat, keep):
     gx = gemm.linear_x3(x2d, w_ih, b_ih)                         # (B*T, 2*3H) fp32
     out = torch.empty((b, t, 2 * h), dtype=F32, device=feat.device)
     gates = torch.empty((b, t, 2, 4, h), dtype=F32, device=feat.device)
-    sync_ws = torch.empty(2 * ((b + 31) // 32) + 2, dtype=torch.int32, device=feat.device)
+    sync_ws = torch.empty(4 * ((b + 31) // 32) + 4, dtype=torch.int32, device=feat.device)
     with torch.cuda.device(feat.device):
         call('sed_gru_fwd', gx.data_ptr(), w_hh.data_ptr(), b_hh.data_ptr(), out.data_ptr(), gates.data_ptr(),
              sync_ws.data_ptr(), b, t, h, stream_of(feat))
