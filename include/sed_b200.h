@@ -83,6 +83,12 @@ int sed_conv3x3_tc_grid(int B, int H, int W, int Cin, int Cout);
  * x = dY, wpack = the dgrad pack and Cin/Cout swapped. */
 int sed_conv3x3_tc_fwd(const void* x, const void* wpack, void* y, float* stats_partial, int B, int H,
                        int W, int Cin, int Cout, sed_stream_t stream);
+/* The same convolution on CTA pairs (tcgen05.mma.cta_group::2, M = 256 per instruction; each CTA stages half of the
+ * weight tile).  Same arguments and results as sed_conv3x3_tc_fwd; statistics workspace rows
+ * from sed_conv3x3_tc2_grid. */
+int sed_conv3x3_tc2_grid(int B, int H, int W, int Cin, int Cout);
+int sed_conv3x3_tc2_fwd(const void* x, const void* wpack, void* y, float* stats_partial, int B, int H, int W, int Cin,
+                        int Cout, sed_stream_t stream);
 /* Data gradient fused with the FIRST pass of the BatchNorm+ReLU(+2x2 avg-pool) backward of the layer below
  * (F.relu_(bn(conv(x))) [+ F.avg_pool2d], pytorch/models.py:102-113): dx (B,H,W,Cout) is that layer's dA; y_below is
  * its raw conv output (B, Hy, W*pool, Cout) with Hy/pool == H (an odd Hy has a floor-mode tail row), scale/shift

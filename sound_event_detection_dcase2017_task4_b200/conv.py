@@ -23,6 +23,10 @@ def pack_weights(w_oihw, want_fwd=True, want_dgrad=True):
     return fwd, dg
 
 
+# CTA-pair (tcgen05.mma.cta_group::2) kernel: measured 33.9 vs 35.7 ms/step (tools/ab_step.py conv.USE_2CTA=0,1)
+USE_2CTA = True
+
+
 def conv3x3(x, wpack, cout, want_stats=False):
     """x (B,H,W,Cin) bf16, wpack [cout, 9*Cin] bf16 -> y (B,H,W,cout) bf16
     [, stats_partial (grid, 2, cout) fp32]."""
@@ -31,12 +35,13 @@ def conv3x3(x, wpack, cout, want_stats=False):
     assert wpack.shape == (cout, 9 * cin) and wpack.dtype == torch.bfloat16 and wpack.is_contiguous()
     y = torch.empty((b, h, w, cout), dtype=torch.bfloat16, device=x.device)
     stats = None
+    pair = USE_2CTA
     with torch.cuda.device(x.device):
         if want_stats:
-            grid = _lib.lib().sed_conv3x3_tc_grid(b, h, w, cin, cout)
+            grid = getattr(_lib.lib(), 'sed_conv3x3_tc2_grid' if pair else 'sed_conv3x3_tc_grid')(b, h, w, cin, cout)
             stats = torch.empty((grid, 2, cout), dtype=torch.float32, device=x.device)
-        _lib.call('sed_conv3x3_tc_fwd', x.data_ptr(), wpack.data_ptr(), y.data_ptr(), _lib.ptr(stats),
-                  b, h, w, cin, cout, _lib.stream_of(x))
+        _lib.call('sed_conv3x3_tc2_fwd' if pair else 'sed_conv3x3_tc_fwd', x.data_ptr(), wpack.data_ptr(), y.data_ptr(),
+                  _lib.ptr(stats), b, h, w, cin, cout, _lib.stream_of(x))
     return (y, stats) if want_stats else y
 
 

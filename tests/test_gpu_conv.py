@@ -108,3 +108,33 @@ def test_conv_dgrad_with_fused_bn_reduce(B, H, W, Cin, Cout, pool):
     got = partial.double().sum(dim=0)
     scale = want.abs().max(dim=1, keepdim=True).values + 1e-6
     assert ((got - want).abs() / scale).max().item() <= 2e-4
+
+
+@pytest.mark.parametrize('B,H,W,Cin,Cout', SHAPES + [
+    (3, 50, 32, 128, 64),      # block2.conv1 data gradient (N = 64 with streamed weights)
+    (2, 25, 16, 256, 128),     # block3.conv1 data gradient
+    (150, 12, 8, 256, 256),    # more pair tiles than CTA pairs: persistent loop + accumulator double buffering
+    (1, 3, 64, 64, 64),        # a single pair tile, mostly tail rows
+])
+def test_conv_cta_pair_kernel(B, H, W, Cin, Cout):
+    """tcgen05.mma.cta_group::2 variant (sed_conv3x3_tc2_fwd): same outputs as the single-CTA kernel (identical
+    accumulation order per output element => bit-equal), statistics equal to a PyTorch fp32 evaluation."""
+    from sound_event_detection_dcase2017_task4_b200 import conv
+    x = _rand((B, H, W, Cin), 21).cuda().to(torch.bfloat16)
+    w = (_rand((Cout, Cin, 3, 3), 22) * (2.0 / (9 * Cin)) ** 0.5).cuda()
+    wf, _ = conv.pack_weights(w)
+    was = conv.USE_2CTA
+    try:
+        conv.USE_2CTA = False
+        y1, s1 = conv.conv3x3(x, wf, Cout, want_stats=True)
+        conv.USE_2CTA = True
+        y2, s2 = conv.conv3x3(x, wf, Cout, want_stats=True)
+        torch.cuda.synchronize()
+    finally:
+        conv.USE_2CTA = was
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), padding=1).permute(0, 2, 3, 1)
+    err = (y2.float() - ref).abs().max().item()
+    assert err <= BF16_EPS * ref.abs().max().item() + 1e-3, err
+    assert torch.equal(y1, y2)
+    a, b = s1.double().sum(0), s2.double().sum(0)
+    assert ((a - b).abs() / (a.abs() + 1.0)).max().item() <= 1e-5

@@ -32,8 +32,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--batch', type=int, default=64)
     ap.add_argument('--what', default='logmel,conv')
+    ap.add_argument('--pair', action='store_true', help='use the cta_group::2 conv kernel where it applies')
     args = ap.parse_args()
     what = args.what.split(',')
+    conv.USE_2CTA = args.pair
     B = args.batch
     if 'logmel' in what:
         melW = torch.from_numpy(fe.mel_weight_matrix(32000, 1024, 64, 50, 14000)).cuda()
