@@ -100,6 +100,9 @@ int sed_conv3x3_tc_dgrad_bnr(const void* dy, const void* wpack_dgrad, void* dx, 
 /* weight gradient: slabs = [sed_conv3x3_tc_wgrad_splits()][9][Cout][Cin] fp32 split-K partials;
  * sed_conv_unpack_wgrad sums them (fixed order) into the OIHW fp32 gradient. */
 int sed_conv3x3_tc_wgrad_splits(int B, int H, int W, int Cin, int Cout);
+/* development switch: 1 (default) = CTA-pair kernel for Cout >= 256 / Cin >= 128, 0 = single-CTA kernel; returns the
+ * previous setting.  Process-wide; meant for tests and A/B timing. */
+int sed_conv3x3_tc_wgrad_use_pairs(int on);
 int sed_conv3x3_tc_wgrad(const void* dy, const void* x, float* slabs, int B, int H, int W, int Cin,
                          int Cout, sed_stream_t stream);
 int sed_conv_unpack_wgrad(const float* g_tap_major, int slabs, long long slab_stride, int Cout, int Cin,

@@ -32,6 +32,7 @@ SIGNATURES = {
     'sed_conv3x3_tc2_fwd': [P, P, P, P, I, I, I, I, I, P],
     'sed_conv3x3_tc_dgrad_bnr': [P, P, P, I, I, I, I, I, P, I, P, P, I, P, P],
     'sed_conv3x3_tc_wgrad_splits': [I, I, I, I, I],
+    'sed_conv3x3_tc_wgrad_use_pairs': [I],
     'sed_conv3x3_tc_wgrad': [P, P, P, I, I, I, I, I, P],
     'sed_conv_unpack_wgrad': [P, I, L, I, I, P, I, P],
     'sed_f32_to_bf16': [P, P, L, P],

@@ -340,9 +340,141 @@ conv3x3_wgrad_kw_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __gri
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The kw-group weight gradient on CTA PAIRS (tcgen05.mma.cta_group::2) for Cout >= 256, Cin >= 128:
+// one M = 256 MMA covers two 128-row Cout tiles (cluster rank r loads the dY slabs of tile 2*pair + r) and the
+// N = 128 Cin tile is split between the CTAs: each one stages only ONE 64-channel X halo slab.  Per SM and K16 step
+// that is 4 KB (A) + 2 KB (B) of operand reads instead of 4 + 4, and 52 KB instead of 72 KB through TMA per
+// 128-pixel stage -- shared-memory bandwidth is what bounds the single-CTA kernel (ncu: TC pipe 83-87 % busy at
+// ~60 % of the MMA peak).  Barrier protocol as in conv_halo2_tc.cu.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsW, 1)
+conv3x3_wgrad_kw2_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
+                         const KwParams p) {
+  constexpr int kN = 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[4], empty_bar[4], done_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  int rest = blockIdx.x >> 1;                       // pair index
+  const int split = rest % p.splits; rest /= p.splits;
+  const int n_tile = rest % p.n_tiles; rest /= p.n_tiles;
+  const int m_pair = rest % (p.m_tiles / 2);
+  const int kw = rest / (p.m_tiles / 2);
+  const int m_tile = 2 * m_pair + (int)rank;
+  const int per = (p.k_total + p.splits - 1) / p.splits;
+  const int k_begin = split * per;
+  const int k_end = min(p.k_total, k_begin + per);
+  const uint32_t x_slab_bytes = (uint32_t)p.x_rows * 128u;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmap_dy);
+    tma_prefetch_desc(&tmap_x);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2cta<512>(&tmem_base_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t bytes = 2u * kSlabBytes + x_slab_bytes;     // per CTA
+      for (int kt = k_begin; kt < k_end; ++kt) {
+        const int b = kt / p.tiles_h;
+        const int h0 = (kt % p.tiles_h) * p.bh;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * p.stage_bytes;
+        uint8_t* sx = sa + 2 * kSlabBytes;
+        if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * bytes);
+        for (int s = 0; s < 2; ++s)
+          tma_load_4d_2cta(sa + s * kSlabBytes, &tmap_dy, &full_bar[stage], m_tile * 128 + s * 64, -(kw - 1), h0, b);
+        tma_load_4d_2cta(sx, &tmap_x, &full_bar[stage], n_tile * kN + (int)rank * 64, 0, h0 - 1, b);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, kN, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kt = k_begin; kt < k_end; ++kt) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * p.stage_bytes);
+        const uint32_t sx = sa + 2 * kSlabBytes;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const uint32_t sxk = sx + (uint32_t)(kh * p.W) * 128u;      // halo tile starts at image row h0 - 1
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {                            // 128 pixels = 8 x K16
+            const uint64_t da = umma_desc_sw128(sa + ks * 2048, kSlabBytes, 1024);
+            const uint64_t db = umma_desc_sw128(sxk + ks * 2048, x_slab_bytes, 1024);
+            umma_bf16_2cta(tmem_base + kh * kN, da, db, idesc, (kt > k_begin || ks > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit_2cta(&empty_bar[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit_2cta(&done_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;                    // accumulator row = output channel within this CTA's tile
+    const int co = m_tile * 128 + row;
+    const bool have = k_end > k_begin;
+    if (have) {
+      mbar_wait(&done_bar, 0);
+      tcgen05_fence_after();
+    }
+#pragma unroll 1
+    for (int kh = 0; kh < 3; ++kh) {
+      const int tap = kh * 3 + kw;
+      float* dst = p.out + (long long)split * p.slab_stride + ((long long)tap * p.Cout + co) * p.Cin + n_tile * kN;
+#pragma unroll 1
+      for (int c = 0; c < kN / 32; ++c) {
+        float v[32];
+        if (have) {
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + kh * kN + c * 32, v);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+        float4* d4 = reinterpret_cast<float4*>(dst + c * 32);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) d4[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc_2cta<512>(tmem_base);
+  }
+}
+
 struct KwPlan {
   int kN, kw_groups, m_tiles, n_tiles, splits, stages, stage_bytes, x_rows, pair, bh, tiles_h, k_total;
+  int cta2;     // CTA-pair kernel (Cout >= 256, Cin >= 128): one X slab per CTA
 };
+
+bool g_wgrad_cta2 = true;
 
 KwPlan make_kw_plan(int B, int H, int W, int Cin, int Cout) {
   KwPlan q;
@@ -355,11 +487,14 @@ KwPlan make_kw_plan(int B, int H, int W, int Cin, int Cout) {
   q.tiles_h = (H + q.bh - 1) / q.bh;
   q.k_total = B * q.tiles_h;
   q.x_rows = 128 + 2 * W;
-  q.stage_bytes = 2 * kSlabBytes + (q.kN / 64) * q.x_rows * 128;
+  q.cta2 = (g_wgrad_cta2 && Cout % 256 == 0 && q.kN == 128) ? 1 : 0;
+  q.stage_bytes = 2 * kSlabBytes + (q.cta2 ? 1 : q.kN / 64) * q.x_rows * 128;
   q.stages = (232448 - 2048) / q.stage_bytes;
   if (q.stages > 4) q.stages = 4;
-  const int items = q.kw_groups * q.m_tiles * q.n_tiles;
-  long long splits = (2LL * sm_count() + items - 1) / items;      // ~2 CTAs worth of work per SM
+  // One CTA per SM fits (shared memory), so the grid must not exceed ONE wave: with ceil(2 * SMs / items) splits
+  // most layers launched 297-336 CTAs on 148 SMs, i.e. a nearly empty third wave (+50 % time).
+  const int items = q.kw_groups * q.m_tiles * q.n_tiles;               // CTAs per split (pairs count as 2 CTAs)
+  long long splits = sm_count() / items;
   if (splits > q.k_total) splits = q.k_total;
   if (splits < 1) splits = 1;
   q.splits = (int)splits;
@@ -391,6 +526,13 @@ int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const WgradParam
 using namespace sed;
 
 extern "C" {
+
+// Development switch (tests / A-B timing): 0 = single-CTA weight-gradient kernel everywhere, 1 = CTA pairs where they apply.
+int sed_conv3x3_tc_wgrad_use_pairs(int on) {
+  const int was = g_wgrad_cta2 ? 1 : 0;
+  g_wgrad_cta2 = on != 0;
+  return was;
+}
 
 // Number of split-K slabs sed_conv3x3_tc_wgrad will write for this shape (workspace sizing).
 int sed_conv3x3_tc_wgrad_splits(int B, int H, int W, int Cin, int Cout) {
@@ -432,6 +574,13 @@ int sed_conv3x3_tc_wgrad(const void* dy, const void* x, float* slabs, int B, int
     if (int rc = tc::make_tmap_bf16(&tx, x, 4, dims, strides, box, "wgrad X halo map")) return rc;
   }
   cudaStream_t s = (cudaStream_t)stream;
+  if (q.cta2) {
+    const int smem = p.stages * p.stage_bytes + 1024;
+    SED_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_kw2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    conv3x3_wgrad_kw2_kernel<<<grid, kThreadsW, smem, s>>>(tdy, tx, p);      // grid = pairs x 2: m_tiles is even here
+    SED_LAUNCH_CHECK("conv3x3_wgrad_kw2_kernel");
+    return 0;
+  }
   if (q.kN == 128) return launch_wgrad_kw<128>(tdy, tx, p, grid, s);
   return launch_wgrad_kw<64>(tdy, tx, p, grid, s);
 }
@@ -444,7 +593,7 @@ int sed_gemm_tn_tc_splits(long long R, int M, int N) {
   const int kN = N >= 128 ? 128 : 64;
   const int items = ((M + 127) / 128) * (N / kN);
   const long long k_total = (R + 127) / 128;
-  long long splits = (2LL * sm_count() + items - 1) / items;
+  long long splits = sm_count() / items;                         // one wave (one CTA fits per SM)
   if (splits > k_total) splits = k_total;
   if (splits < 1) splits = 1;
   return (int)splits;

@@ -138,3 +138,21 @@ def test_conv_cta_pair_kernel(B, H, W, Cin, Cout):
     assert torch.equal(y1, y2)
     a, b = s1.double().sum(0), s2.double().sum(0)
     assert ((a - b).abs() / (a.abs() + 1.0)).max().item() <= 1e-5
+
+
+@pytest.mark.parametrize('B,H,W,Cin,Cout', [(2, 25, 16, 128, 256), (2, 25, 16, 256, 256), (2, 12, 8, 256, 512),
+                                            (1, 125, 8, 512, 512), (40, 25, 16, 256, 256)])
+def test_conv_wgrad_cta_pair_kernel(B, H, W, Cin, Cout):
+    """cta_group::2 weight-gradient kernel vs the single-CTA one (same accumulation order => bit-equal)."""
+    from sound_event_detection_dcase2017_task4_b200 import _lib, conv
+    x = _rand((B, H, W, Cin), 31).cuda().to(torch.bfloat16)
+    dy = _rand((B, H, W, Cout), 32).cuda().to(torch.bfloat16)
+    was = _lib.lib().sed_conv3x3_tc_wgrad_use_pairs(0)
+    try:
+        single = conv.conv3x3_wgrad(dy, x)
+        _lib.lib().sed_conv3x3_tc_wgrad_use_pairs(1)
+        pair = conv.conv3x3_wgrad(dy, x)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().sed_conv3x3_tc_wgrad_use_pairs(was)
+    assert torch.equal(single, pair)
