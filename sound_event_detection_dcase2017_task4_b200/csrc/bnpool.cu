@@ -330,7 +330,9 @@ __global__ void __launch_bounds__(kRowThreads, 3)
 bn_bwd_reduce_flat_kernel(const __nv_bfloat16* __restrict__ y, const void* __restrict__ dA_,
                           const float* __restrict__ scale, const float* __restrict__ shift,
                           const float* __restrict__ mean, const float* __restrict__ invstd, long long nvec, int C,
-                          float* __restrict__ partial) {
+                          int row_shift, float row_scale, float* __restrict__ partial) {
+  // row_shift >= 0: "pool over the whole row" (block 4: 1 x W average = torch.mean(x, dim=3)): dA is (rows, C) and
+  // vector v of y belongs to row v >> row_shift (W * C/8 is a power of two), g = dA / W
   extern __shared__ float s_red[];                 // [lanes][2*C]
   const int CV = C >> 3, cv = threadIdx.x % CV, pl = threadIdx.x / CV, lanes = kRowThreads / CV;
   float sc[8], sh[8], mu[8], is[8], sg[8], sgx[8];
@@ -345,12 +347,13 @@ bn_bwd_reduce_flat_kernel(const __nv_bfloat16* __restrict__ y, const void* __res
   for (long long v = (long long)blockIdx.x * kRowThreads + threadIdx.x; v < nvec; v += stride) {
     float g[8], x[8];
     const uint4 raw = ldg16(y + v * 8);
-    if (kGradF32) load8f(reinterpret_cast<const float*>(dA_) + v * 8, g);
-    else unpack8(ldg16(reinterpret_cast<const __nv_bfloat16*>(dA_) + v * 8), g);
+    const long long gv = row_shift >= 0 ? ((v >> row_shift) * CV + cv) : v;
+    if (kGradF32) load8f(reinterpret_cast<const float*>(dA_) + gv * 8, g);
+    else unpack8(ldg16(reinterpret_cast<const __nv_bfloat16*>(dA_) + gv * 8), g);
     unpack8(raw, x);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float gk = fmaf(x[k], sc[k], sh[k]) > 0.f ? g[k] : 0.f;
+      const float gk = fmaf(x[k], sc[k], sh[k]) > 0.f ? g[k] * row_scale : 0.f;
       sg[k] += gk;
       sgx[k] += gk * (x[k] - mu[k]) * is[k];
     }
@@ -373,7 +376,8 @@ __global__ void __launch_bounds__(kRowThreads, 3)
 bn_bwd_apply_flat_kernel(const __nv_bfloat16* __restrict__ y, const void* __restrict__ dA_,
                          const float* __restrict__ scale, const float* __restrict__ shift,
                          const float* __restrict__ mean, const float* __restrict__ invstd,
-                         const float* __restrict__ coef, long long nvec, int C, __nv_bfloat16* __restrict__ dy) {
+                         const float* __restrict__ coef, long long nvec, int C, int row_shift, float row_scale,
+                         __nv_bfloat16* __restrict__ dy) {
   const int CV = C >> 3, cv = threadIdx.x % CV;
   float sc[8], sh[8], cA[8], cB[8], cC[8];
   {
@@ -389,6 +393,7 @@ bn_bwd_apply_flat_kernel(const __nv_bfloat16* __restrict__ y, const void* __rest
     for (int k = 0; k < 8; ++k) {
       cB[k] = -cA[k] * c3[k] * is[k];
       cC[k] = -cA[k] * c2[k] - cB[k] * mu[k];
+      cA[k] *= row_scale;
     }
   }
   const long long stride = (long long)gridDim.x * kRowThreads;
@@ -396,8 +401,9 @@ bn_bwd_apply_flat_kernel(const __nv_bfloat16* __restrict__ y, const void* __rest
   for (long long v = (long long)blockIdx.x * kRowThreads + threadIdx.x; v < nvec; v += stride) {
     float g[8], x[8], o[8];
     const uint4 raw = ldg16(y + v * 8);
-    if (kGradF32) load8f(reinterpret_cast<const float*>(dA_) + v * 8, g);
-    else unpack8(ldg16(reinterpret_cast<const __nv_bfloat16*>(dA_) + v * 8), g);
+    const long long gv = row_shift >= 0 ? ((v >> row_shift) * CV + cv) : v;
+    if (kGradF32) load8f(reinterpret_cast<const float*>(dA_) + gv * 8, g);
+    else unpack8(ldg16(reinterpret_cast<const __nv_bfloat16*>(dA_) + gv * 8), g);
     unpack8(raw, x);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -552,7 +558,15 @@ bool rows_path_ok(int H, int W, int C, int ph, int pw) {
   const int CV = C / 8;
   if (C % 8 != 0 || CV < 1 || CV > kRowThreads || kRowThreads % CV != 0) return false;
   if (ph == 1 && pw == 1) return true;
+  if (ph == 1 && pw == W) return ((W * CV) & (W * CV - 1)) == 0;      // whole-row average (block 4 + mean over mel)
   return ph == 2 && pw == 2 && W % 2 == 0 && H >= 2;
+}
+// log2(W * C/8) for the whole-row pooling form of the flat kernels, -1 for the un-pooled form
+int row_pool_shift(int W, int C, int pw) {
+  if (pw == 1) return -1;
+  int n = W * (C / 8), s = 0;
+  while ((1 << s) < n) ++s;
+  return s;
 }
 // one full wave: `per_sm` CTAs of 256 threads are co-resident per SM (set by __launch_bounds__), so every
 // CTA walks the same number of rows and there is no partial second wave
@@ -605,7 +619,7 @@ int sed_bn_relu_pool_fwd(const void* y, const float* scale, const float* shift, 
   const long long total = (long long)B * (H / ph) * (W / pw) * (C / 8);
   const int grid = ew_grid(total, 256);
   const __nv_bfloat16* yy = reinterpret_cast<const __nv_bfloat16*>(y);
-  if (!out_is_f32 && rows_path_ok(H, W, C, ph, pw) && (long long)B * H < (1LL << 31)) {
+  if (!out_is_f32 && ph == pw && rows_path_ok(H, W, C, ph, pw) && (long long)B * H < (1LL << 31)) {
     __nv_bfloat16* oo = reinterpret_cast<__nv_bfloat16*>(out);
     const int g = rows_grid(B * (H / ph), 4);
     if (ph == 1) bn_relu_fwd_flat_kernel<<<sm_count() * 4, kRowThreads, 0, (cudaStream_t)stream>>>(yy, scale, shift, (long long)B * H * W * (C / 8), C, oo);
@@ -639,8 +653,10 @@ int sed_bn_relu_pool_bwd_reduce(const void* y, const void* dA, int grad_is_f32, 
     cudaStream_t st = (cudaStream_t)stream;
     const long long nvec = (long long)B * H * W * (C / 8);
     if (ph == 1) {
-      if (grad_is_f32) bn_bwd_reduce_flat_kernel<true><<<grid, kRowThreads, smem, st>>>(yy, dA, scale, shift, mean, invstd, nvec, C, partial);
-      else bn_bwd_reduce_flat_kernel<false><<<grid, kRowThreads, smem, st>>>(yy, dA, scale, shift, mean, invstd, nvec, C, partial);
+      const int rs = row_pool_shift(W, C, pw);
+      const float rsc = pw == 1 ? 1.0f : 1.0f / (float)pw;
+      if (grad_is_f32) bn_bwd_reduce_flat_kernel<true><<<grid, kRowThreads, smem, st>>>(yy, dA, scale, shift, mean, invstd, nvec, C, rs, rsc, partial);
+      else bn_bwd_reduce_flat_kernel<false><<<grid, kRowThreads, smem, st>>>(yy, dA, scale, shift, mean, invstd, nvec, C, rs, rsc, partial);
     }
     else if (grad_is_f32) bn_bwd_reduce_win2_kernel<true><<<grid, kRowThreads, smem, st>>>(yy, dA, scale, shift, mean, invstd, B, H, W, C, partial);
     else bn_bwd_reduce_win2_kernel<false><<<grid, kRowThreads, smem, st>>>(yy, dA, scale, shift, mean, invstd, B, H, W, C, partial);
@@ -682,8 +698,10 @@ int sed_bn_relu_pool_bwd_apply(const void* y, const void* dA, int grad_is_f32, c
     const long long nvec = (long long)B * H * W * (C / 8);
     if (ph == 1) {
       const int gf = sm_count() * 3;
-      if (grad_is_f32) bn_bwd_apply_flat_kernel<true><<<gf, kRowThreads, 0, st>>>(yy, dA, scale, shift, mean, invstd, coef, nvec, C, dd);
-      else bn_bwd_apply_flat_kernel<false><<<gf, kRowThreads, 0, st>>>(yy, dA, scale, shift, mean, invstd, coef, nvec, C, dd);
+      const int rs = row_pool_shift(W, C, pw);
+      const float rsc = pw == 1 ? 1.0f : 1.0f / (float)pw;
+      if (grad_is_f32) bn_bwd_apply_flat_kernel<true><<<gf, kRowThreads, 0, st>>>(yy, dA, scale, shift, mean, invstd, coef, nvec, C, rs, rsc, dd);
+      else bn_bwd_apply_flat_kernel<false><<<gf, kRowThreads, 0, st>>>(yy, dA, scale, shift, mean, invstd, coef, nvec, C, rs, rsc, dd);
     }
     else {
       const int g2 = rows_grid(B * (H / 2), 3);
