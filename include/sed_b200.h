@@ -216,13 +216,13 @@ int sed_gru_bwd(const float* dout, const float* out, const float* gates, const f
  * w_vs projections used in place (replaces the four permute().contiguous() copies).  T <= 128, d = 64.
  * ctx (B*T, H*64); probs (B,H,T,T) = softmax before dropout (saved for the backward, may be NULL).
  * Dropout(p_drop) on the probabilities from Philox4x32-10(seed, offset + element/4); p_drop = 0 in eval.
- * bwd: ds_scratch (B,H,T,T) workspace; dq/dk/dv use the addressing of q/k/v. */
+ * bwd: dq/dk/dv use the addressing of q/k/v. */
 int sed_attention_fwd(const float* q, const float* k, const float* v, int ldq, int ldk, int ldv, int B, int T, int H,
                       int d, float temperature, float p_drop, unsigned long long seed, unsigned long long offset,
                       float* ctx, float* probs, sed_stream_t stream);
 int sed_attention_bwd(const float* q, const float* k, const float* v, int ldq, int ldk, int ldv, int B, int T, int H,
                       int d, float temperature, float p_drop, unsigned long long seed, unsigned long long offset,
-                      const float* dctx, const float* probs, float* ds_scratch, float* dq, float* dk, float* dv,
+                      const float* dctx, const float* probs, float* dq, float* dk, float* dv,
                       sed_stream_t stream);
 /* y = relu(dropout_p(x)) (models.py:664) and its backward dx = dy * [y > 0] / (1 - p). */
 int sed_dropout_relu_fwd(const float* x, long long n, float p_drop, unsigned long long seed, unsigned long long offset,

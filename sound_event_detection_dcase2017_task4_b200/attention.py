@@ -91,11 +91,10 @@ def multihead_backward(mh, mctx, dfeat, grad_of):
             gemm.colsum(do, g)
         dctx = gemm.gemm_nt(do16, gemm.transpose_bf16(mh.fc.weight))                  # (B*T, h*d)
         dqkv = torch.empty((b * t, ld), dtype=F32, device=dev)
-        scratch = torch.empty((b, h, t, t), dtype=F32, device=dev)
         qb, gb = mctx.qkv.data_ptr(), dqkv.data_ptr()
         call('sed_attention_bwd', qb, qb + 4 * h * d, qb + 8 * h * d, ld, ld, ld, b, t, h, d,
              float(mh.attention.temperature), mctx.p_att, mctx.seed, mctx.off_att, dctx.data_ptr(),
-             mctx.probs.data_ptr(), scratch.data_ptr(), gb, gb + 4 * h * d, gb + 8 * h * d, s)
+             mctx.probs.data_ptr(), gb, gb + 4 * h * d, gb + 8 * h * d, s)
         dqkv16, x16 = tcconv.to_bf16(dqkv), tcconv.to_bf16(mctx.x2d)
         db = torch.empty(ld, dtype=F32, device=dev)
         gemm.colsum(dqkv, db)

@@ -76,10 +76,9 @@ def test_attention_kernel_exact_fp32_parts():
     dctx = torch.randn(B * T, H * d, generator=g).cuda()
     ctx_ref.backward(dctx)
     dqkv = torch.empty_like(qkv)
-    scratch = torch.empty_like(probs)
     gb = dqkv.data_ptr()
     call('sed_attention_bwd', base, base + 4 * H * d, base + 8 * H * d, ld, ld, ld, B, T, H, d, 8.0, 0.0, 0, 0,
-         dctx.data_ptr(), probs.data_ptr(), scratch.data_ptr(), gb, gb + 4 * H * d, gb + 8 * H * d, stream_of(qkv))
+         dctx.data_ptr(), probs.data_ptr(), gb, gb + 4 * H * d, gb + 8 * H * d, stream_of(qkv))
     assert torch.allclose(dqkv, ref_in.grad, rtol=1e-3, atol=1e-5)
 
 
