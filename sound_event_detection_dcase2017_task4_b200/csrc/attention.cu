@@ -69,8 +69,8 @@ attention_fwd_kernel(AttParams p, float* __restrict__ ctx, float* __restrict__ p
   extern __shared__ float smem[];
   float* sK = smem;                         // [T][kLdK]
   float* sV = sK + kMaxT * kLdK;            // [T][kD]
-  float* sQ = sV + kMaxT * kD;              // [kWarps][kD]
-  float* sP = sQ + kWarps * kD;             // [kWarps][kMaxT]
+  float* sQ = sV + kMaxT * kD;              // [kWarps * 4][kD]     the warp's block of query rows
+  float* sP = sQ + kWarps * 4 * kD;         // [kWarps * 4][kMaxT]  their probability rows
   const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
   const int T = p.T;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -82,58 +82,98 @@ attention_fwd_kernel(AttParams p, float* __restrict__ ctx, float* __restrict__ p
   }
   __syncthreads();
   const float keep_scale = p.p_drop > 0.f ? 1.0f / (1.0f - p.p_drop) : 1.0f;
-  for (int i = warp; i < T; i += kWarps) {
-    const long long row = (long long)b * T + i;
-    sQ[warp * kD + lane] = p.q[row * p.ldq + h * kD + lane];
-    sQ[warp * kD + lane + 32] = p.q[row * p.ldq + h * kD + lane + 32];
-    __syncwarp();
-    float s[kMaxT / 32];
-    float mx = -INFINITY;
+  // kFB query rows per warp iteration: every K / V element read from shared memory serves kFB rows
+  constexpr int kFB = 4;
+  for (int i0 = warp * kFB; i0 < T; i0 += kWarps * kFB) {
 #pragma unroll
-    for (int c = 0; c < kMaxT / 32; ++c) {
-      const int j = lane + 32 * c;
-      float a = 0.f;
-      if (j < T) {
-        const float* kr = sK + j * kLdK;
-        const float* qr = sQ + warp * kD;
-#pragma unroll 16
-        for (int d = 0; d < kD; ++d) a = fmaf(qr[d], kr[d], a);
-        a *= p.inv_temp;
-        mx = fmaxf(mx, a);
+    for (int r = 0; r < kFB; ++r) {
+      const int i = i0 + r;
+      float q0 = 0.f, q1 = 0.f;
+      if (i < T) {
+        const long long row = (long long)b * T + i;
+        q0 = p.q[row * p.ldq + h * kD + lane];
+        q1 = p.q[row * p.ldq + h * kD + lane + 32];
       }
-      s[c] = a;
-    }
-    mx = warp_max(mx);
-    float sum = 0.f;
-#pragma unroll
-    for (int c = 0; c < kMaxT / 32; ++c) {
-      const int j = lane + 32 * c;
-      s[c] = j < T ? expf(s[c] - mx) : 0.f;
-      sum += s[c];
-    }
-    sum = warp_sum(sum);
-    const float inv = 1.0f / sum;
-    const long long pbase = (((long long)b * p.H + h) * T + i) * T;
-#pragma unroll
-    for (int c = 0; c < kMaxT / 32; ++c) {
-      const int j = lane + 32 * c;
-      if (j < T) {
-        float pr = s[c] * inv;
-        if (probs) probs[pbase + j] = pr;
-        if (p.p_drop > 0.f) pr = keep_elem(p.seed, p.offset, (unsigned long long)(pbase + j), p.p_drop) ? pr * keep_scale : 0.f;
-        sP[warp * kMaxT + j] = pr;
-      }
+      sQ[(warp * kFB + r) * kD + lane] = q0;
+      sQ[(warp * kFB + r) * kD + lane + 32] = q1;
     }
     __syncwarp();
-    float o0 = 0.f, o1 = 0.f;
-    const float* pr = sP + warp * kMaxT;
+    float s[kFB][kMaxT / 32];
+#pragma unroll
+    for (int r = 0; r < kFB; ++r)
+#pragma unroll
+      for (int c = 0; c < kMaxT / 32; ++c) s[r][c] = 0.f;
+    const float* qr = sQ + warp * kFB * kD;
+#pragma unroll 4
+    for (int d = 0; d < kD; ++d) {
+      float kk[kMaxT / 32], qq[kFB];
+#pragma unroll
+      for (int c = 0; c < kMaxT / 32; ++c) kk[c] = sK[min(lane + 32 * c, T - 1) * kLdK + d];
+#pragma unroll
+      for (int r = 0; r < kFB; ++r) qq[r] = qr[r * kD + d];
+#pragma unroll
+      for (int r = 0; r < kFB; ++r)
+#pragma unroll
+        for (int c = 0; c < kMaxT / 32; ++c) s[r][c] = fmaf(qq[r], kk[c], s[r][c]);
+    }
+#pragma unroll
+    for (int r = 0; r < kFB; ++r) {
+      const int i = i0 + r;
+      if (i >= T) break;                                    // warp-uniform
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < kMaxT / 32; ++c) {
+        const int j = lane + 32 * c;
+        s[r][c] *= p.inv_temp;
+        if (j < T) mx = fmaxf(mx, s[r][c]);
+      }
+      mx = warp_max(mx);
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < kMaxT / 32; ++c) {
+        const int j = lane + 32 * c;
+        s[r][c] = j < T ? expf(s[r][c] - mx) : 0.f;
+        sum += s[r][c];
+      }
+      sum = warp_sum(sum);
+      const float inv = 1.0f / sum;
+      const long long pbase = (((long long)b * p.H + h) * T + i) * T;
+#pragma unroll
+      for (int c = 0; c < kMaxT / 32; ++c) {
+        const int j = lane + 32 * c;
+        float pr = 0.f;
+        if (j < T) {
+          pr = s[r][c] * inv;
+          if (probs) probs[pbase + j] = pr;
+          if (p.p_drop > 0.f) pr = keep_elem(p.seed, p.offset, (unsigned long long)(pbase + j), p.p_drop) ? pr * keep_scale : 0.f;
+        }
+        sP[(warp * kFB + r) * kMaxT + j] = pr;
+      }
+    }
+    __syncwarp();
+    float o0[kFB], o1[kFB];
+#pragma unroll
+    for (int r = 0; r < kFB; ++r) o0[r] = o1[r] = 0.f;
+    const float* pr = sP + warp * kFB * kMaxT;
+    const int nr = min(kFB, T - i0);
     for (int j = 0; j < T; ++j) {
-      const float w = pr[j];
-      o0 = fmaf(w, sV[j * kD + lane], o0);
-      o1 = fmaf(w, sV[j * kD + lane + 32], o1);
+      const float va = sV[j * kD + lane], vb = sV[j * kD + lane + 32];
+#pragma unroll
+      for (int r = 0; r < kFB; ++r) {
+        const float w = pr[min(r, nr - 1) * kMaxT + j];
+        o0[r] = fmaf(w, va, o0[r]);
+        o1[r] = fmaf(w, vb, o1[r]);
+      }
     }
-    ctx[row * (p.H * kD) + h * kD + lane] = o0;
-    ctx[row * (p.H * kD) + h * kD + lane + 32] = o1;
+#pragma unroll
+    for (int r = 0; r < kFB; ++r) {
+      const int i = i0 + r;
+      if (i < T) {
+        const long long row = (long long)b * T + i;
+        ctx[row * (p.H * kD) + h * kD + lane] = o0[r];
+        ctx[row * (p.H * kD) + h * kD + lane + 32] = o1[r];
+      }
+    }
     __syncwarp();
   }
 }
@@ -347,7 +387,7 @@ int sed_attention_fwd(const float* q, const float* k, const float* v, int ldq, i
   SED_REQUIRE(p_drop >= 0.f && p_drop < 1.f && temperature > 0.f, "sed_attention_fwd: bad scalars");
   if (B == 0) return 0;
   AttParams p{q, k, v, ldq, ldk, ldv, B, T, H, 1.0f / temperature, p_drop, seed, offset};
-  const size_t smem = sizeof(float) * (size_t)(kMaxT * kLdK + kMaxT * kD + kWarps * kD + kWarps * kMaxT);
+  const size_t smem = sizeof(float) * (size_t)(kMaxT * kLdK + kMaxT * kD + kWarps * 4 * kD + kWarps * 4 * kMaxT);
   SED_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   attention_fwd_kernel<<<B * H, kAttThreads, smem, (cudaStream_t)stream>>>(p, ctx, probs);
   SED_LAUNCH_CHECK("attention_fwd_kernel");
