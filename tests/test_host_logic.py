@@ -153,3 +153,33 @@ def test_launcher_resolves_reference_imports_to_the_dropin():
         "print('ok')\n" % (ROOT, ref, ref))
     r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.strip().endswith('ok'), r.stderr[-2000:]
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under the product package may import it (a product path that routes
+    through the oracle would void every parity claim)."""
+    pkg = os.path.join(ROOT, 'sound_event_detection_dcase2017_task4_b200')
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith('.py'):
+                with open(os.path.join(dirpath, f)) as fh:
+                    for n, line in enumerate(fh, 1):
+                        if re.match(r'\s*(from|import)\s+oracle\b', line):
+                            offenders.append('%s:%d' % (os.path.join(dirpath, f), n))
+    assert offenders == []
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU oracle on the host cores) prints one JSON line with the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([x for x in r.stdout.splitlines() if x.startswith('{')][-1])
+    assert line['impl'] == 'reference' and line['unit'] == 'clips/s' and line['higher_is_better'] is True
+    assert line['value'] > 0 and line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
+    assert line['e2e'] == {'value': line['value'], 'unit': 'clips/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert 'Cnn_9layers_Gru_FrameAtt' in line['metric'] and 'Cnn_9layers_Gru_FrameAtt' in line['config']['workload']
