@@ -183,3 +183,34 @@ def test_reference_arm_prints_the_contract_line():
     assert line['value'] > 0 and line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
     assert line['e2e'] == {'value': line['value'], 'unit': 'clips/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert 'Cnn_9layers_Gru_FrameAtt' in line['metric'] and 'Cnn_9layers_Gru_FrameAtt' in line['config']['workload']
+
+
+def test_abi_rejects_bad_arguments_before_touching_the_device():
+    """Error contract of the C ABI (include/sed_b200.h): non-zero status, a thread-local message, no exception and --
+    for argument errors -- no CUDA call at all, so these run without a GPU."""
+    import threading
+    from sound_event_detection_dcase2017_task4_b200 import _lib
+    L = _lib.lib()
+
+    def msg():
+        return (L.sed_last_error_string() or b'').decode()
+
+    assert L.sed_conv3x3_tc_fwd(0, 0, 0, 0, 1, 10, 16, 64, 64, 0) != 0 and 'null pointer' in msg()
+    buf = ctypes.create_string_buffer(4096)
+    p = ctypes.addressof(buf)
+    assert L.sed_conv3x3_tc_fwd(p, p, p, 0, 1, 10, 12, 64, 64, 0) != 0 and 'W=12' in msg()
+    assert L.sed_conv3x3_tc_fwd(p, p, p, 0, 1, 10, 16, 96, 64, 0) != 0 and 'Cin=96' in msg()
+    assert L.sed_conv3x3_tc2_fwd(p, p, p, 0, 1, 10, 16, 64, 192, 0) != 0 and 'Cout=192' in msg()
+    assert L.sed_logmel_f32(p, 1, 400, 320, p, p, p, 64, 1e-10, 0.0, p, 0) != 0 and 'reflect padding' in msg()
+    assert L.sed_logmel_f32(p, 1, 32000, 321, p, p, p, 64, 1e-10, 0.0, p, 0) != 0 and 'hop must be even' in msg()
+    assert L.sed_vad_count(p, 0, 1, 10, 0, 0, p, 0, p, p, p, 0, 0) != 0 and 'bad shape' in msg()
+    assert L.sed_conv3x3_tc_dgrad_bnr(p, p, p, 1, 10, 16, 64, 64, p, 10, p, p, 3, p, 0) != 0 and 'pool=3' in msg()
+    with pytest.raises(RuntimeError, match='sed_conv3x3_tc_fwd failed'):
+        _lib.call('sed_conv3x3_tc_fwd', 0, 0, 0, 0, 1, 10, 16, 64, 64, 0)
+    # the message is per thread
+    assert L.sed_conv3x3_tc_fwd(p, p, p, 0, 1, 10, 12, 64, 64, 0) != 0
+    seen = []
+    t = threading.Thread(target=lambda: seen.append(msg()))
+    t.start()
+    t.join()
+    assert 'W=12' in msg() and 'W=12' not in seen[0]
