@@ -16,7 +16,7 @@ half of it and is reported as ``train_samples_per_s``.
 One JSON line on stdout (rank 0).  ``value``: inputs resident in HBM; ``e2e``: the same step with
 the waveforms/targets/lambda copied from pinned host memory inside the timed region and the loss
 read back to the host every step.  ``roofline``: the 3x3 tensor-core convolution kernel
-(conv3x3_tc_kernel: all forward + data-gradient launches of a step) against the measured bf16
+(conv3x3_halo2_kernel, CTA pairs: all forward + data-gradient launches of a step) against the measured bf16
 peak.  ``cpu_baseline`` / ``--impl reference``: the CPU oracle (oracle/sed.py, a restatement of
 the reference's PyTorch modules pinned to the unmodified reference by tests/golden) timed on
 this box's host cores on a bounded sample of the same workload.
@@ -316,7 +316,7 @@ def run_ours(args):
         shares = {k: {'launches_per_step': v[0] // reps, 'ms_per_step': round(v[1] / reps, 4),
                       'share': round(v[1] / reps / total_ms, 4)}
                   for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])}
-        # conv3x3_tc_kernel runs the forward of 7 layers and the data-gradient of 6 (block1.conv2's
+        # the conv kernel runs the forward of 7 layers and the data-gradient of 7 (block1.conv2's
         # dgrad feeds the Cin=1 layer; block1.conv1 itself is a separate direct kernel)
         fl = [2.0 * h * w * ci * co * 9 for (h, w, ci, co) in CONV_TC_LAYERS]
         flops_step = bs * (sum(fl) + sum(fl))           # fwd + dgrad of all 7 tensor-core layers

@@ -1,4 +1,4 @@
-"""Launch wrappers for the tensor-core 3x3 convolution family (csrc/conv_tc.cu,
+"""Launch wrappers for the tensor-core 3x3 convolution family (csrc/conv_halo2_tc.cu, csrc/conv_halo_tc.cu,
 csrc/conv_wgrad_tc.cu, csrc/pack.cu).  Tensors are NHWC bf16 (B, H, W, C)."""
 import torch
 

@@ -1,4 +1,4 @@
-// conv_tc.cu -- plain tensor-core GEMM on the one-box-per-K-block tcgen05 pipeline (sm_100a):
+// gemm_tc.cu -- plain tensor-core GEMM on the one-box-per-K-block tcgen05 pipeline (sm_100a):
 //   out[M][N] = A[M][K] * Bw[N][K]^T (+ bias),  A / Bw bf16 K-major, out fp32.
 // Used for the GRU / attention projections (x @ W^T) of /root/reference/pytorch/models.py:475/:566 (nn.GRU input
 // projection) and :641-665 (MultiHead), optionally with the 3-way bf16 operand split (sed_split_bf16x3) for
@@ -29,25 +29,20 @@ template <int kN> struct Cfg {
   static constexpr int kDynSmem = kStages * kStageBytes + 1024;   // +1024 for manual alignment
 };
 
-struct ConvParams {
-  int B, H, W, Cin, Cout;
-  int bh;            // tile height in pixels; bh * W == 128
-  int tiles_h;       // ceil(H / bh)
-  int tiles_n;       // Cout / kN
-  int num_tiles;     // B * tiles_h * tiles_n
-  int kb_per_tap;    // Cin / 64
-  __nv_bfloat16* y;  // NHWC output
-  float* stats;      // [gridDim.x][2][Cout] partial (sum, sumsq) or nullptr
-  // plain-GEMM mode (kGemm): D[M][N] = A[M][K] * B[N][K]^T (+ bias[N]), fp32 row-major output
+struct GemmParams {
+  int N;             // columns of the output
+  int tiles_m;       // ceil(M / 128)
+  int tiles_n;       // N / kN
+  int num_tiles;     // tiles_m * tiles_n
   int gemm_m, gemm_kb;        // rows of A, K / 64
-  float* out_f32;
+  float* out_f32;    // D[M][N] = A[M][K] * B[N][K]^T (+ bias[N]), fp32 row-major
   const float* bias;
 };
 
-template <int kN, bool kGemm>
+template <int kN>
 __global__ void __launch_bounds__(kNumThreads, 1)
-conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  const ConvParams p) {
+gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const GemmParams p) {
   using C = Cfg<kN>;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle needs 1024 B aligned tiles
@@ -145,7 +140,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       {
         const long long m = (long long)m_tile * kBlockM + row;
         const bool ok = m < p.gemm_m;
-        float* drow = p.out_f32 + m * p.Cout + n_tile * kN;
+        float* drow = p.out_f32 + m * p.N + n_tile * kN;
 #pragma unroll 1
         for (int c = half; c < kN / 32; c += 2) {
           float v[32];
@@ -173,12 +168,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   }
 }
 
-template <int kN, bool kGemm = false>
-int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, int grid, cudaStream_t stream) {
-  auto kern = conv3x3_tc_kernel<kN, kGemm>;
+template <int kN>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid, cudaStream_t stream) {
+  auto kern = gemm_nt_tc_kernel<kN>;
   SED_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<kN>::kDynSmem));
   kern<<<grid, kNumThreads, Cfg<kN>::kDynSmem, stream>>>(ta, tb, p);
-  SED_LAUNCH_CHECK("conv3x3_tc_kernel");
+  SED_LAUNCH_CHECK("gemm_nt_tc_kernel");
   return 0;
 }
 
@@ -200,14 +195,11 @@ int sed_gemm_tc(const void* a, const void* bw, const float* bias, float* out, lo
   SED_REQUIRE(N == 64 || N == 128 || N % 256 == 0, "sed_gemm_tc: N=%d unsupported", N);
   SED_REQUIRE(aligned(out, 16), "sed_gemm_tc: output must be 16-byte aligned");
   const int kN = N >= 256 ? 256 : N;
-  ConvParams p;
-  p.B = 1; p.H = 1; p.W = 128; p.Cin = K; p.Cout = N;
-  p.bh = 1;
-  p.tiles_h = (int)((M + 127) / 128);
+  GemmParams p;
+  p.N = N;
+  p.tiles_m = (int)((M + 127) / 128);
   p.tiles_n = N / kN;
-  p.num_tiles = p.tiles_h * p.tiles_n;
-  p.kb_per_tap = 0;
-  p.y = nullptr; p.stats = nullptr;
+  p.num_tiles = p.tiles_m * p.tiles_n;
   p.gemm_m = (int)M; p.gemm_kb = K / 64; p.out_f32 = out; p.bias = bias;
   const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   alignas(64) CUtensorMap ta, tb;
@@ -225,9 +217,9 @@ int sed_gemm_tc(const void* a, const void* bw, const float* bias, float* out, lo
   }
   cudaStream_t s = (cudaStream_t)stream;
   switch (kN) {
-    case 64: return launch_conv<64, true>(ta, tb, p, grid, s);
-    case 128: return launch_conv<128, true>(ta, tb, p, grid, s);
-    case 256: return launch_conv<256, true>(ta, tb, p, grid, s);
+    case 64: return launch_gemm<64>(ta, tb, p, grid, s);
+    case 128: return launch_gemm<128>(ta, tb, p, grid, s);
+    case 256: return launch_gemm<256>(ta, tb, p, grid, s);
   }
   SED_REQUIRE(false, "sed_gemm_tc: no kernel for N tile %d", kN);
 }

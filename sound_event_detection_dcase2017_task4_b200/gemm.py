@@ -1,5 +1,5 @@
 """Launch wrappers for the plain tensor-core GEMMs and their precision / layout helpers
-(csrc/conv_tc.cu sed_gemm_tc, csrc/conv_wgrad_tc.cu sed_gemm_tn_tc, csrc/gru.cu helpers)."""
+(csrc/gemm_tc.cu sed_gemm_tc, csrc/conv_wgrad_tc.cu sed_gemm_tn_tc, csrc/gru.cu helpers)."""
 import torch
 
 from . import _lib
