@@ -122,18 +122,27 @@ int sed_bn_eval_affine(const float* running_mean, const float* running_var, cons
                        float eps, int C, float* scale, float* shift, sed_stream_t stream);
 int sed_bn_relu_pool_fwd(const void* y, const float* scale, const float* shift, int B, int H, int W, int C, int ph,
                          int pw, void* out, int out_is_f32, sed_stream_t stream);
-int sed_bn_bwd_partials(int C);
+/* Backward of the same stage in two passes over y (no saved activation other than y itself):
+ *   reduce   -> partial[P][2][C] = per-worker sums of g and g*y,  g = unpool(dA)/(ph*pw) * [y*scale + shift > 0],
+ *               P = sed_bn_bwd_partials(shape);
+ *   finalize -> dgamma, dbeta, coef[3][C] (pass the layer's batch mean as mean_for_gy);
+ *   apply    -> dY = gamma*invstd * (g - mean(g) - xhat*mean(g*xhat))   (bf16).
+ * The fast paths (pool 1x1, 1xW, 2x2; C/4 a power of two) are dynamically scheduled persistent kernels built to share
+ * an SM with a weight-gradient CTA (<= 64 registers, 4 KB shared memory): `sched` points to TWO int32 words that are
+ * zero before the call and zero again after it (one pair per stream that runs these kernels concurrently). */
+int sed_bn_bwd_partials(int B, int H, int W, int C, int ph, int pw);
 int sed_bn_relu_pool_bwd_reduce(const void* y, const void* dA, int grad_is_f32, const float* scale,
-                                const float* shift, const float* mean, const float* invstd, int B, int H, int W,
-                                int C, int ph, int pw, float* partial, sed_stream_t stream);
-/* mean_for_gy: NULL when the second partial column holds sum(g*xhat) (sed_bn_relu_pool_bwd_reduce); the layer's
- * batch mean when it holds sum(g*y) (sed_conv3x3_tc_dgrad_bnr): sum(g*xhat) = invstd*(sum(g*y) - mean*sum(g)). */
+                                const float* shift, int B, int H, int W, int C, int ph, int pw, float* partial,
+                                int* sched, sed_stream_t stream);
+/* mean_for_gy: NULL when the second partial column holds sum(g*xhat) (sed_bn0_bwd_reduce); the layer's batch mean
+ * when it holds sum(g*y) (sed_bn_relu_pool_bwd_reduce, sed_conv3x3_tc_dgrad_bnr):
+ * sum(g*xhat) = invstd*(sum(g*y) - mean*sum(g)). */
 int sed_bn_bwd_finalize(const float* partial, int P, int C, double count, const float* gamma, const float* invstd,
                         const float* mean_for_gy, float* dgamma, float* dbeta, int accumulate, float* coef,
                         sed_stream_t stream);
 int sed_bn_relu_pool_bwd_apply(const void* y, const void* dA, int grad_is_f32, const float* scale, const float* shift,
                                const float* mean, const float* invstd, const float* coef, int B, int H, int W, int C,
-                               int ph, int pw, void* dy, sed_stream_t stream);
+                               int ph, int pw, void* dy, int* sched, sed_stream_t stream);
 
 /* ---- bn0 + SpecAugment + mixup (pytorch/models.py:202-211, pytorch_utils.py:80-93) ------------
  * stripes: int32 (B2, n, 2) = (begin, width), drawn on the host in torchlibrosa's RNG order. */

@@ -39,10 +39,10 @@ SIGNATURES = {
     'sed_bn_finalize': [P, I, I, D, P, P, F, F, P, P, P, P, P, P, P, P],
     'sed_bn_eval_affine': [P, P, P, P, F, I, P, P, P],
     'sed_bn_relu_pool_fwd': [P, P, P, I, I, I, I, I, I, P, I, P],
-    'sed_bn_bwd_partials': [I],
-    'sed_bn_relu_pool_bwd_reduce': [P, P, I, P, P, P, P, I, I, I, I, I, I, P, P],
+    'sed_bn_bwd_partials': [I, I, I, I, I, I],
+    'sed_bn_relu_pool_bwd_reduce': [P, P, I, P, P, I, I, I, I, I, I, P, P, P],
     'sed_bn_bwd_finalize': [P, I, I, D, P, P, P, P, P, I, P, P],
-    'sed_bn_relu_pool_bwd_apply': [P, P, I, P, P, P, P, P, I, I, I, I, I, I, P, P],
+    'sed_bn_relu_pool_bwd_apply': [P, P, I, P, P, P, P, P, I, I, I, I, I, I, P, P, P],
     'sed_stat_partials': [],
     'sed_colstats_f32': [P, L, I, P, P],
     'sed_bn0_aug_mix_fwd': [P, P, P, P, I, P, I, P, I, I, I, P, P],

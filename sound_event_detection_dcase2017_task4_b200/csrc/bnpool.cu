@@ -15,6 +15,7 @@
 //   sed_bn_bwd_finalize         -> dgamma, dbeta and the three per-channel coefficients
 //   sed_bn_relu_pool_bwd_apply  -> dY = gamma*invstd * (g - mean(g) - xhat*mean(g*xhat))      (bf16)
 #include "common.cuh"
+#include <string.h>
 
 namespace sed {
 namespace {
@@ -123,7 +124,6 @@ __global__ void bn_relu_pool_fwd_kernel(const __nv_bfloat16* __restrict__ y, con
 template <bool kGradF32>
 __global__ void bn_relu_pool_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ y, const void* __restrict__ dA_,
                                                const float* __restrict__ scale, const float* __restrict__ shift,
-                                               const float* __restrict__ mean, const float* __restrict__ invstd,
                                                int B, int H, int W, int C, int ph, int pw,
                                                float* __restrict__ partial) {
   extern __shared__ float s_red[];                       // [lanes][2*C]
@@ -134,11 +134,9 @@ __global__ void bn_relu_pool_bwd_reduce_kernel(const __nv_bfloat16* __restrict__
   const long long per = (npix + gridDim.x - 1) / gridDim.x;
   const long long p0 = blockIdx.x * per, p1 = min(npix, p0 + per);
   const float inv = 1.0f / (float)(ph * pw);
-  float sc[8], sh[8], mu[8], is[8], sg[8], sgx[8];
+  float sc[8], sh[8], sg[8], sgx[8];
   load8f(scale + cv * kVec, sc);
   load8f(shift + cv * kVec, sh);
-  load8f(mean + cv * kVec, mu);
-  load8f(invstd + cv * kVec, is);
 #pragma unroll
   for (int k = 0; k < 8; ++k) sg[k] = sgx[k] = 0.f;
   if (pl < lanes) {
@@ -159,7 +157,7 @@ __global__ void bn_relu_pool_bwd_reduce_kernel(const __nv_bfloat16* __restrict__
         const float act = fmaf(v[k], sc[k], sh[k]);
         const float gk = act > 0.f ? g[k] * inv : 0.f;
         sg[k] += gk;
-        sgx[k] += gk * (v[k] - mu[k]) * is[k];
+        sgx[k] = fmaf(gk, v[k], sgx[k]);               // raw y: sed_bn_bwd_finalize converts with the batch mean
       }
     }
   }
@@ -325,233 +323,300 @@ bn_relu_fwd_flat_kernel(const __nv_bfloat16* __restrict__ y, const float* __rest
   }
 }
 
-template <bool kGradF32>
-__global__ void __launch_bounds__(kRowThreads, 3)
-bn_bwd_reduce_flat_kernel(const __nv_bfloat16* __restrict__ y, const void* __restrict__ dA_,
-                          const float* __restrict__ scale, const float* __restrict__ shift,
-                          const float* __restrict__ mean, const float* __restrict__ invstd, long long nvec, int C,
-                          int row_shift, float row_scale, float* __restrict__ partial) {
-  // row_shift >= 0: "pool over the whole row" (block 4: 1 x W average = torch.mean(x, dim=3)): dA is (rows, C) and
-  // vector v of y belongs to row v >> row_shift (W * C/8 is a power of two), g = dA / W
-  extern __shared__ float s_red[];                 // [lanes][2*C]
-  const int CV = C >> 3, cv = threadIdx.x % CV, pl = threadIdx.x / CV, lanes = kRowThreads / CV;
-  float sc[8], sh[8], mu[8], is[8], sg[8], sgx[8];
-  load8f(scale + cv * 8, sc);
-  load8f(shift + cv * 8, sh);
-  load8f(mean + cv * 8, mu);
-  load8f(invstd + cv * 8, is);
-#pragma unroll
-  for (int k = 0; k < 8; ++k) sg[k] = sgx[k] = 0.f;
-  const long long stride = (long long)gridDim.x * kRowThreads;
-#pragma unroll 4
-  for (long long v = (long long)blockIdx.x * kRowThreads + threadIdx.x; v < nvec; v += stride) {
-    float g[8], x[8];
-    const uint4 raw = ldg16(y + v * 8);
-    const long long gv = row_shift >= 0 ? ((v >> row_shift) * CV + cv) : v;
-    if (kGradF32) load8f(reinterpret_cast<const float*>(dA_) + gv * 8, g);
-    else unpack8(ldg16(reinterpret_cast<const __nv_bfloat16*>(dA_) + gv * 8), g);
-    unpack8(raw, x);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float gk = fmaf(x[k], sc[k], sh[k]) > 0.f ? g[k] * row_scale : 0.f;
-      sg[k] += gk;
-      sgx[k] += gk * (x[k] - mu[k]) * is[k];
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    s_red[pl * 2 * C + cv * 8 + k] = sg[k];
-    s_red[pl * 2 * C + C + cv * 8 + k] = sgx[k];
-  }
+// ================================================================ backward fast paths (round 2)
+// Co-residency-friendly, dynamically scheduled versions.  The weight-gradient kernel of layer l (tensor-pipe bound, one
+// 192-thread CTA per SM holding ~210 KB of shared memory) only depends on dY_l, while the BatchNorm backward of layer
+// l-1 (HBM bound) is the next link of the critical chain; engine.trunk_backward runs the two on different streams.
+// For them to really share an SM these kernels
+//   * stay at <= 64 registers / thread (a thread owns FOUR channels = 8-byte vectors, so the per-channel constants of
+//     the apply pass fit), i.e. 3 CTAs fit beside a weight-gradient CTA, 4 when alone;
+//   * use 4 KB of shared memory (the reduction scratch), which fits in what the weight-gradient kernel leaves free;
+//   * take their work from an atomic ticket counter instead of assuming a full resident wave: a *virtual worker* w owns
+//     a fixed contiguous range of vectors / pooled rows whatever CTA executes it, so the per-worker partial sums -- and
+//     with them the fixed-order fp64 finalize -- stay bit-reproducible under any co-scheduling.  Worker sizes are
+//     two-tier (the last quarter of the tensor is cut into 4x smaller workers) to keep the tail short.
+// The reduction pass produces sum(g) and sum(g*y) (raw y); sed_bn_bwd_finalize converts with the batch mean.
+constexpr int kDynThreads = 256;
+
+struct DynPlan {
+  long long n_units;      // flat: blocks of 1024 four-channel vectors; win2: pooled rows
+  long long big, small;   // units per worker in the two tiers
+  int v_big, V;
+};
+
+__device__ __forceinline__ void dyn_range(const DynPlan& q, int w, long long& u0, long long& u1) {
+  if (w < q.v_big) { u0 = (long long)w * q.big; u1 = u0 + q.big; }
+  else { u0 = (long long)q.v_big * q.big + (long long)(w - q.v_big) * q.small; u1 = u0 + q.small; }
+  if (u1 > q.n_units) u1 = q.n_units;
+  if (u0 > u1) u0 = u1;
+}
+// ticket of the next virtual worker (block-uniform).  sched[0] = next ticket, sched[1] = CTAs that ran dry; both are
+// zero before the launch and the last CTA to run dry re-zeroes them, so consecutive launches can share the words.
+__device__ __forceinline__ int dyn_next(int* sched) {
+  __shared__ int s_ticket;
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += kRowThreads) {
-    float a = 0.f;
-    for (int l = 0; l < lanes; ++l) a += s_red[l * 2 * C + i];
-    partial[(long long)blockIdx.x * 2 * C + i] = a;
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&sched[0], 1);
+  __syncthreads();
+  return s_ticket;
+}
+__device__ __forceinline__ void dyn_retire(int* sched) {
+  if (threadIdx.x == 0) {
+    const int d = atomicAdd(&sched[1], 1);
+    if (d == (int)gridDim.x - 1) { atomicExch(&sched[0], 0); atomicExch(&sched[1], 0); }
   }
 }
 
+__device__ __forceinline__ uint2 ldg8(const void* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+__device__ __forceinline__ void unpack4(const uint2& raw, float (&v)[4]) {
+  const float2 a = unpack_bf16x2(raw.x), b = unpack_bf16x2(raw.y);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void store4(__nv_bfloat16* p, const float (&v)[4]) {
+  uint2 o;
+  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = o;
+}
+__device__ __forceinline__ void load4f(const float* p, float (&v)[4]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
 template <bool kGradF32>
-__global__ void __launch_bounds__(kRowThreads, 3)
-bn_bwd_apply_flat_kernel(const __nv_bfloat16* __restrict__ y, const void* __restrict__ dA_,
-                         const float* __restrict__ scale, const float* __restrict__ shift,
-                         const float* __restrict__ mean, const float* __restrict__ invstd,
-                         const float* __restrict__ coef, long long nvec, int C, int row_shift, float row_scale,
-                         __nv_bfloat16* __restrict__ dy) {
-  const int CV = C >> 3, cv = threadIdx.x % CV;
-  float sc[8], sh[8], cA[8], cB[8], cC[8];
-  {
-    float mu[8], is[8], c2[8], c3[8];
-    load8f(scale + cv * 8, sc);
-    load8f(shift + cv * 8, sh);
-    load8f(mean + cv * 8, mu);
-    load8f(invstd + cv * 8, is);
-    load8f(coef + cv * 8, cA);
-    load8f(coef + C + cv * 8, c2);
-    load8f(coef + 2 * C + cv * 8, c3);
+__device__ __forceinline__ void load_grad4(const void* dA, long long vec, float (&g)[4]) {
+  if (kGradF32) load4f(reinterpret_cast<const float*>(dA) + vec * 4, g);
+  else unpack4(ldg8(reinterpret_cast<const __nv_bfloat16*>(dA) + vec * 4), g);
+}
+
+// per-worker partial row: partial[w][0][c] = sum g, partial[w][1][c] = sum g*y.  Thread (pl, cv) holds 4 channels of
+// lane pl; the `lanes` = 256 / (C/4) lanes are summed in fixed order through a 4 KB scratch, one statistic at a time.
+__device__ __forceinline__ void dyn_write_partial(float* s_red, const float (&sg)[4], const float (&sgy)[4], int C, int cv,
+                                                  int pl, int lanes, float* __restrict__ row) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+  for (int pass = 0; pass < 2; ++pass) {
+    if (pass) __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s_red[pl * C + cv * 4 + k] = pass ? sgy[k] : sg[k];
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += kDynThreads) {
+      float a = 0.f;
+      for (int l = 0; l < lanes; ++l) a += s_red[l * C + i];
+      row[pass * C + i] = a;
+    }
+  }
+}
+
+// ---- un-pooled layers (and block 4's whole-row average): y, dA, dY are one flat stream of 8-byte vectors
+template <bool kGradF32>
+__global__ void __launch_bounds__(kDynThreads, 4)
+bn_bwd_reduce_flat4_kernel(const __nv_bfloat16* __restrict__ y, const void* __restrict__ dA_,
+                           const float* __restrict__ scale, const float* __restrict__ shift, long long nvec, int C,
+                           int row_shift, float row_scale, DynPlan q, float* __restrict__ partial, int* sched) {
+  __shared__ float s_red[kDynThreads * 4];
+  const int CV = C >> 2, cv = threadIdx.x & (CV - 1), pl = threadIdx.x / CV, lanes = kDynThreads / CV;
+  float sc[4], sh[4];
+  load4f(scale + cv * 4, sc);
+  load4f(shift + cv * 4, sh);
+  for (;;) {
+    const int w = dyn_next(sched);
+    if (w >= q.V) break;
+    long long u0, u1;
+    dyn_range(q, w, u0, u1);
+    const long long v1 = min(nvec, u1 * 1024);
+    float sg[4] = {0.f, 0.f, 0.f, 0.f}, sgy[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (long long v = u0 * 1024 + threadIdx.x; v < v1; v += kDynThreads) {
+      const uint2 raw = ldg8(y + v * 4);
+      const long long gv = row_shift >= 0 ? ((v >> row_shift) * CV + cv) : v;
+      float g[4], x[4];
+      load_grad4<kGradF32>(dA_, gv, g);
+      unpack4(raw, x);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float gk = fmaf(x[k], sc[k], sh[k]) > 0.f ? g[k] * row_scale : 0.f;
+        sg[k] += gk;
+        sgy[k] = fmaf(gk, x[k], sgy[k]);
+      }
+    }
+    dyn_write_partial(s_red, sg, sgy, C, cv, pl, lanes, partial + (long long)w * 2 * C);
+  }
+  dyn_retire(sched);
+}
+
+template <bool kGradF32>
+__global__ void __launch_bounds__(kDynThreads, 4)
+bn_bwd_apply_flat4_kernel(const __nv_bfloat16* __restrict__ y, const void* __restrict__ dA_,
+                          const float* __restrict__ scale, const float* __restrict__ shift,
+                          const float* __restrict__ mean, const float* __restrict__ invstd,
+                          const float* __restrict__ coef, long long nvec, int C, int row_shift, float row_scale,
+                          DynPlan q, __nv_bfloat16* __restrict__ dy, int* sched) {
+  const int CV = C >> 2, cv = threadIdx.x & (CV - 1);
+  float sc[4], sh[4], cA[4], cB[4], cC[4];
+  {
+    float mu[4], is[4], c2[4], c3[4];
+    load4f(scale + cv * 4, sc);
+    load4f(shift + cv * 4, sh);
+    load4f(mean + cv * 4, mu);
+    load4f(invstd + cv * 4, is);
+    load4f(coef + cv * 4, cA);
+    load4f(coef + C + cv * 4, c2);
+    load4f(coef + 2 * C + cv * 4, c3);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
       cB[k] = -cA[k] * c3[k] * is[k];
       cC[k] = -cA[k] * c2[k] - cB[k] * mu[k];
       cA[k] *= row_scale;
     }
   }
-  const long long stride = (long long)gridDim.x * kRowThreads;
+  for (;;) {
+    const int w = dyn_next(sched);
+    if (w >= q.V) break;
+    long long u0, u1;
+    dyn_range(q, w, u0, u1);
+    const long long v1 = min(nvec, u1 * 1024);
 #pragma unroll 4
-  for (long long v = (long long)blockIdx.x * kRowThreads + threadIdx.x; v < nvec; v += stride) {
-    float g[8], x[8], o[8];
-    const uint4 raw = ldg16(y + v * 8);
-    const long long gv = row_shift >= 0 ? ((v >> row_shift) * CV + cv) : v;
-    if (kGradF32) load8f(reinterpret_cast<const float*>(dA_) + gv * 8, g);
-    else unpack8(ldg16(reinterpret_cast<const __nv_bfloat16*>(dA_) + gv * 8), g);
-    unpack8(raw, x);
+    for (long long v = u0 * 1024 + threadIdx.x; v < v1; v += kDynThreads) {
+      const uint2 raw = ldg8(y + v * 4);
+      const long long gv = row_shift >= 0 ? ((v >> row_shift) * CV + cv) : v;
+      float g[4], x[4], o[4];
+      load_grad4<kGradF32>(dA_, gv, g);
+      unpack4(raw, x);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float gk = fmaf(x[k], sc[k], sh[k]) > 0.f ? g[k] : 0.f;
-      o[k] = fmaf(cA[k], gk, fmaf(cB[k], x[k], cC[k]));
+      for (int k = 0; k < 4; ++k) {
+        const float gk = fmaf(x[k], sc[k], sh[k]) > 0.f ? g[k] : 0.f;
+        o[k] = fmaf(cA[k], gk, fmaf(cB[k], x[k], cC[k]));
+      }
+      store4(dy + v * 4, o);
     }
-    store8(dy + v * 8, o);
   }
+  dyn_retire(sched);
 }
 
-// ---- 2x2-pool backward, window-structured: a thread-iteration owns one pooled output vector (8 channels) and
-// its 2x2 window of y: ONE dA load + FOUR y loads in flight (instead of 4 x (1 + 1) with the dA vector fetched by
-// four different threads), no integer division, and the floor-mode tail row (odd H) is handled separately.
+// ---- 2x2-pooled layers: a thread-iteration owns one pooled gradient vector (4 channels) and its 2x2 window of y.
+// A worker owns a range of pooled rows (b, ho); its (row, vector) pairs are walked as one flat index so that two
+// independent iterations (2 x (1 + 4) loads) are in flight whatever the row length.  ov_shift = log2(Wo * C/4).
 template <bool kGradF32>
-__global__ void __launch_bounds__(kRowThreads, 3)
-bn_bwd_reduce_win2_kernel(const __nv_bfloat16* __restrict__ y, const void* __restrict__ dA_,
-                          const float* __restrict__ scale, const float* __restrict__ shift,
-                          const float* __restrict__ mean, const float* __restrict__ invstd, int B, int H, int W,
-                          int C, float* __restrict__ partial) {
-  extern __shared__ float s_red[];                 // [lanes][2*C]
-  const int CV = C >> 3, Ho = H >> 1, Wo = W >> 1;
-  const int cv = threadIdx.x % CV, pl = threadIdx.x / CV, lanes = kRowThreads / CV, cv_shift = __ffs(CV) - 1;
-  float sc[8], sh[8], mu[8], is[8], sg[8], sgx[8];
-  load8f(scale + cv * 8, sc);
-  load8f(shift + cv * 8, sh);
-  load8f(mean + cv * 8, mu);
-  load8f(invstd + cv * 8, is);
-#pragma unroll
-  for (int k = 0; k < 8; ++k) sg[k] = sgx[k] = 0.f;
-  const int out_vecs = Wo * CV;
+__global__ void __launch_bounds__(kDynThreads, 4)
+bn_bwd_reduce_win4_kernel(const __nv_bfloat16* __restrict__ y, const void* __restrict__ dA_,
+                          const float* __restrict__ scale, const float* __restrict__ shift, int H, int W, int C,
+                          int ov_shift, DynPlan q, float* __restrict__ partial, int* sched) {
+  __shared__ float s_red[kDynThreads * 4];
+  const int CV = C >> 2, Ho = H >> 1, cv = threadIdx.x & (CV - 1), pl = threadIdx.x / CV, lanes = kDynThreads / CV;
+  const int cv_shift = __ffs(CV) - 1;
   const long long in_row = (long long)W * C;
-  const int rows = B * Ho;
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    const int b = row / Ho, ho = row - b * Ho;
-    const __nv_bfloat16* src = y + ((long long)b * H + 2LL * ho) * in_row;
-    const long long drow = (long long)row * Wo * C;
-#pragma unroll 1
-    for (int v = threadIdx.x; v < out_vecs; v += kRowThreads) {
-      const int wo = v >> cv_shift;
-      const long long x0 = ((long long)(2 * wo) * CV + cv) * 8;
-      uint4 raw[4];
-      raw[0] = ldg16(src + x0);
-      raw[1] = ldg16(src + x0 + C);
-      raw[2] = ldg16(src + in_row + x0);
-      raw[3] = ldg16(src + in_row + x0 + C);
-      float g[8];
-      if (kGradF32) load8f(reinterpret_cast<const float*>(dA_) + drow + (long long)v * 8, g);
-      else { const uint4 graw = ldg16(reinterpret_cast<const __nv_bfloat16*>(dA_) + drow + (long long)v * 8); unpack8(graw, g); }
+  const int ov_mask = (1 << ov_shift) - 1;
+  float sc[4], sh[4];
+  load4f(scale + cv * 4, sc);
+  load4f(shift + cv * 4, sh);
+  for (;;) {
+    const int w = dyn_next(sched);
+    if (w >= q.V) break;
+    long long u0, u1;
+    dyn_range(q, w, u0, u1);
+    const long long j1 = (u1 - u0) << ov_shift;
+    float sg[4] = {0.f, 0.f, 0.f, 0.f}, sgy[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+    for (long long j = threadIdx.x; j < j1; j += kDynThreads) {
+      const int row = (int)(u0 + (j >> ov_shift)), v = (int)j & ov_mask;
+      const int b = row / Ho, ho = row - b * Ho, wo = v >> cv_shift;
+      const __nv_bfloat16* src = y + ((long long)b * H + 2LL * ho) * in_row + ((long long)(2 * wo) * CV + cv) * 4;
+      uint2 raw[4];
+      raw[0] = ldg8(src);
+      raw[1] = ldg8(src + C);
+      raw[2] = ldg8(src + in_row);
+      raw[3] = ldg8(src + in_row + C);
+      float g[4];
+      load_grad4<kGradF32>(dA_, ((long long)row << ov_shift) + v, g);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) g[k] *= 0.25f;
+      for (int k = 0; k < 4; ++k) g[k] *= 0.25f;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        float x[8];
-        unpack8(raw[i], x);
+        float x[4];
+        unpack4(raw[i], x);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float act = fmaf(x[k], sc[k], sh[k]);
-          const float gk = act > 0.f ? g[k] : 0.f;
+        for (int k = 0; k < 4; ++k) {
+          const float gk = fmaf(x[k], sc[k], sh[k]) > 0.f ? g[k] : 0.f;
           sg[k] += gk;
-          sgx[k] += gk * (x[k] - mu[k]) * is[k];
+          sgy[k] = fmaf(gk, x[k], sgy[k]);
         }
       }
     }
+    dyn_write_partial(s_red, sg, sgy, C, cv, pl, lanes, partial + (long long)w * 2 * C);
   }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    s_red[pl * 2 * C + cv * 8 + k] = sg[k];
-    s_red[pl * 2 * C + C + cv * 8 + k] = sgx[k];
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += kRowThreads) {
-    float a = 0.f;
-    for (int l = 0; l < lanes; ++l) a += s_red[l * 2 * C + i];
-    partial[(long long)blockIdx.x * 2 * C + i] = a;
-  }
+  dyn_retire(sched);
 }
 
 template <bool kGradF32>
-__global__ void __launch_bounds__(kRowThreads, 3)
-bn_bwd_apply_win2_kernel(const __nv_bfloat16* __restrict__ y, const void* __restrict__ dA_,
+__global__ void __launch_bounds__(kDynThreads, 4)
+bn_bwd_apply_win4_kernel(const __nv_bfloat16* __restrict__ y, const void* __restrict__ dA_,
                          const float* __restrict__ scale, const float* __restrict__ shift,
                          const float* __restrict__ mean, const float* __restrict__ invstd,
-                         const float* __restrict__ coef, int B, int H, int W, int C,
-                         __nv_bfloat16* __restrict__ dy) {
-  const int CV = C >> 3, Ho = H >> 1, Wo = W >> 1;
-  const int cv = threadIdx.x % CV, cv_shift = __ffs(CV) - 1;
-  float sc[8], sh[8], cA[8], cB[8], cC[8];
+                         const float* __restrict__ coef, int B, int H, int W, int C, int ov_shift, DynPlan q,
+                         __nv_bfloat16* __restrict__ dy, int* sched) {
+  const int CV = C >> 2, Ho = H >> 1, cv = threadIdx.x & (CV - 1);
+  const int cv_shift = __ffs(CV) - 1;
+  const long long in_row = (long long)W * C;
+  const int ov_mask = (1 << ov_shift) - 1;
+  float sc[4], sh[4], cA[4], cB[4], cC[4];
   {
-    float mu[8], is[8], c1[8], c2[8], c3[8];
-    load8f(scale + cv * 8, sc);
-    load8f(shift + cv * 8, sh);
-    load8f(mean + cv * 8, mu);
-    load8f(invstd + cv * 8, is);
-    load8f(coef + cv * 8, c1);
-    load8f(coef + C + cv * 8, c2);
-    load8f(coef + 2 * C + cv * 8, c3);
+    float mu[4], is[4], c1[4], c2[4], c3[4];
+    load4f(scale + cv * 4, sc);
+    load4f(shift + cv * 4, sh);
+    load4f(mean + cv * 4, mu);
+    load4f(invstd + cv * 4, is);
+    load4f(coef + cv * 4, c1);
+    load4f(coef + C + cv * 4, c2);
+    load4f(coef + 2 * C + cv * 4, c3);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < 4; ++k) {
       cA[k] = c1[k] * 0.25f;
       cB[k] = -c1[k] * c3[k] * is[k];
       cC[k] = -c1[k] * c2[k] - cB[k] * mu[k];
     }
   }
-  const int out_vecs = Wo * CV;
-  const long long in_row = (long long)W * C;
-  const int rows = B * Ho;
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    const int b = row / Ho, ho = row - b * Ho;
-    const long long base = ((long long)b * H + 2LL * ho) * in_row;
-    const long long drow = (long long)row * Wo * C;
-#pragma unroll 1
-    for (int v = threadIdx.x; v < out_vecs; v += kRowThreads) {
-      const int wo = v >> cv_shift;
-      const long long x0 = base + ((long long)(2 * wo) * CV + cv) * 8;
-      const long long offs[4] = {x0, x0 + C, x0 + in_row, x0 + in_row + C};
-      uint4 raw[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) raw[i] = ldg16(y + offs[i]);
-      float g[8];
-      if (kGradF32) load8f(reinterpret_cast<const float*>(dA_) + drow + (long long)v * 8, g);
-      else { const uint4 graw = ldg16(reinterpret_cast<const __nv_bfloat16*>(dA_) + drow + (long long)v * 8); unpack8(graw, g); }
+  for (;;) {
+    const int w = dyn_next(sched);
+    if (w >= q.V) break;
+    long long u0, u1;
+    dyn_range(q, w, u0, u1);
+    const long long j1 = (u1 - u0) << ov_shift;
+#pragma unroll 2
+    for (long long j = threadIdx.x; j < j1; j += kDynThreads) {
+      const int row = (int)(u0 + (j >> ov_shift)), v = (int)j & ov_mask;
+      const int b = row / Ho, ho = row - b * Ho, wo = v >> cv_shift;
+      const long long x0 = ((long long)b * H + 2LL * ho) * in_row + ((long long)(2 * wo) * CV + cv) * 4;
+      uint2 raw[4];
+      raw[0] = ldg8(y + x0);
+      raw[1] = ldg8(y + x0 + C);
+      raw[2] = ldg8(y + x0 + in_row);
+      raw[3] = ldg8(y + x0 + in_row + C);
+      float g[4];
+      load_grad4<kGradF32>(dA_, ((long long)row << ov_shift) + v, g);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        float x[8], o[8];
-        unpack8(raw[i], x);
+        float x[4], o[4];
+        unpack4(raw[i], x);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float act = fmaf(x[k], sc[k], sh[k]);
-          const float gk = act > 0.f ? g[k] : 0.f;
+        for (int k = 0; k < 4; ++k) {
+          const float gk = fmaf(x[k], sc[k], sh[k]) > 0.f ? g[k] : 0.f;
           o[k] = fmaf(cA[k], gk, fmaf(cB[k], x[k], cC[k]));
         }
-        store8(dy + offs[i], o);
+        store4(dy + x0 + (i >> 1) * in_row + (i & 1) * C, o);
       }
     }
-  }
-  if (H & 1) {                                       // floor-mode tail row: no pooled gradient reaches it
-    const int in_vecs = W * CV;
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
-      const long long base = ((long long)b * H + (H - 1)) * in_row;
-      for (int v = threadIdx.x; v < in_vecs; v += kRowThreads) {
-        float x[8], o[8];
-        unpack8(ldg16(y + base + (long long)v * 8), x);
+    if (H & 1) {                                     // floor-mode tail row: no pooled gradient reaches it
+      const int in_vecs = W * CV;
+      for (int b = w; b < B; b += q.V) {
+        const long long base = ((long long)b * H + (H - 1)) * in_row;
+        for (int v = threadIdx.x; v < in_vecs; v += kDynThreads) {
+          float x[4], o[4];
+          unpack4(ldg8(y + base + (long long)v * 4), x);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = fmaf(cB[k], x[k], cC[k]);
-        store8(dy + base + (long long)v * 8, o);
+          for (int k = 0; k < 4; ++k) o[k] = fmaf(cB[k], x[k], cC[k]);
+          store4(dy + base + (long long)v * 4, o);
+        }
       }
     }
   }
+  dyn_retire(sched);
 }
 
 bool rows_path_ok(int H, int W, int C, int ph, int pw) {
@@ -560,6 +625,64 @@ bool rows_path_ok(int H, int W, int C, int ph, int pw) {
   if (ph == 1 && pw == 1) return true;
   if (ph == 1 && pw == W) return ((W * CV) & (W * CV - 1)) == 0;      // whole-row average (block 4 + mean over mel)
   return ph == 2 && pw == 2 && W % 2 == 0 && H >= 2;
+}
+int ilog2(long long n) {
+  int s = 0;
+  while ((1LL << s) < n) ++s;
+  return s;
+}
+bool pow2(long long n) { return n > 0 && (n & (n - 1)) == 0; }
+
+// ---- plan of the dynamically scheduled backward kernels ----------------------------------------------------------
+struct BwdPlan {
+  int kind;          // 0 generic kernels, 1 flat (un-pooled / whole-row pooled), 2 2x2 window
+  int row_shift;     // flat: log2(W * C/4) for whole-row pooling, -1 un-pooled;  win: log2(Wo * C/4)
+  float row_scale;
+  long long nvec;    // flat: four-channel vectors
+  DynPlan q;
+  int grid;
+};
+BwdPlan make_bwd_plan(int B, int H, int W, int C, int ph, int pw) {
+  BwdPlan p;
+  memset(&p, 0, sizeof(p));
+  const int CV = C / 4;
+  const bool c_ok = C % 4 == 0 && CV >= 1 && CV <= kDynThreads && pow2(CV) && C <= kDynThreads * 4;
+  const long long rows = (long long)B * H;
+  long long unit_bytes = 0;
+  if (c_ok && rows < (1LL << 31) && ph == 1 && (pw == 1 || (pw == W && pow2((long long)W * CV)))) {
+    p.kind = 1;
+    p.row_shift = pw == 1 ? -1 : ilog2((long long)W * CV);
+    p.row_scale = pw == 1 ? 1.0f : 1.0f / (float)pw;
+    p.nvec = rows * W * CV;
+    p.q.n_units = (p.nvec + 1023) / 1024;
+    unit_bytes = 1024 * 8;
+  } else if (c_ok && rows < (1LL << 31) && ph == 2 && pw == 2 && W % 2 == 0 && H >= 2 && pow2((long long)(W / 2) * CV)) {
+    p.kind = 2;
+    p.row_shift = ilog2((long long)(W / 2) * CV);
+    p.q.n_units = (long long)B * (H / 2);
+    unit_bytes = 2LL * W * C * 2;
+  } else {
+    p.q.V = sm_count() * 3;          // rows of the partial workspace = grid of the generic reduce kernel
+    p.grid = p.q.V;
+    return p;
+  }
+  // workers of ~768 KB of y (never fewer than 4 per SM, never more than 16 per SM in the first tier); the last quarter
+  // of the tensor goes to workers a quarter of that size
+  const long long n = p.q.n_units;
+  long long big = (768 * 1024) / unit_bytes;
+  const long long lo = (n + sm_count() * 16LL - 1) / (sm_count() * 16LL), hi = n / (sm_count() * 4LL);
+  if (big > hi) big = hi;
+  if (big < lo) big = lo;
+  if (big < 1) big = 1;
+  long long small = big / 4;
+  if (small < 1) small = 1;
+  long long v_big = (n - n / 4) / big;
+  const long long rest = n - v_big * big;
+  const long long v_small = (rest + small - 1) / small;
+  p.q.big = big; p.q.small = small; p.q.v_big = (int)v_big; p.q.V = (int)(v_big + v_small);
+  p.grid = sm_count() * 4;
+  if (p.grid > p.q.V) p.grid = p.q.V;
+  return p;
 }
 // log2(W * C/8) for the whole-row pooling form of the flat kernels, -1 for the un-pooled form
 int row_pool_shift(int W, int C, int pw) {
@@ -635,40 +758,40 @@ int sed_bn_relu_pool_fwd(const void* y, const float* scale, const float* shift, 
   return 0;
 }
 
-int sed_bn_bwd_partials(int C) {   // rows of the partial workspace used by the reduce pass
-  (void)C;
-  return sm_count() * 3;           // = one resident wave of the row-structured reduce kernel (3 CTAs / SM)
+int sed_bn_bwd_partials(int B, int H, int W, int C, int ph, int pw) {   // rows of the partial workspace of the reduce pass
+  if (B < 1 || H < 1 || W < 1 || C < 8) return 0;
+  return make_bwd_plan(B, H, W, C, ph, pw).q.V;
 }
 
 int sed_bn_relu_pool_bwd_reduce(const void* y, const void* dA, int grad_is_f32, const float* scale,
-                                const float* shift, const float* mean, const float* invstd, int B, int H, int W,
-                                int C, int ph, int pw, float* partial, sed_stream_t stream) {
-  SED_REQUIRE(y && dA && scale && shift && mean && invstd && partial, "sed_bn_relu_pool_bwd_reduce: null pointer");
+                                const float* shift, int B, int H, int W, int C, int ph, int pw, float* partial,
+                                int* sched, sed_stream_t stream) {
+  SED_REQUIRE(y && dA && scale && shift && partial && sched, "sed_bn_relu_pool_bwd_reduce: null pointer");
   SED_REQUIRE(C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0, "sed_bn_relu_pool_bwd_reduce: C=%d unsupported", C);
-  const int grid = sed_bn_bwd_partials(C);
-  const int lanes = 256 / (C / 8);
-  const size_t smem = (size_t)lanes * 2 * C * sizeof(float);
+  SED_REQUIRE(B >= 1 && H / ph >= 1 && W / pw >= 1, "sed_bn_relu_pool_bwd_reduce: bad shape");
+  SED_REQUIRE(aligned(y, 16) && aligned(dA, 16) && aligned(scale, 16) && aligned(shift, 16),
+              "sed_bn_relu_pool_bwd_reduce: pointers must be 16-byte aligned");
+  const BwdPlan p = make_bwd_plan(B, H, W, C, ph, pw);
   const __nv_bfloat16* yy = reinterpret_cast<const __nv_bfloat16*>(y);
-  if (rows_path_ok(H, W, C, ph, pw) && (long long)B * H < (1LL << 31)) {
-    cudaStream_t st = (cudaStream_t)stream;
-    const long long nvec = (long long)B * H * W * (C / 8);
-    if (ph == 1) {
-      const int rs = row_pool_shift(W, C, pw);
-      const float rsc = pw == 1 ? 1.0f : 1.0f / (float)pw;
-      if (grad_is_f32) bn_bwd_reduce_flat_kernel<true><<<grid, kRowThreads, smem, st>>>(yy, dA, scale, shift, mean, invstd, nvec, C, rs, rsc, partial);
-      else bn_bwd_reduce_flat_kernel<false><<<grid, kRowThreads, smem, st>>>(yy, dA, scale, shift, mean, invstd, nvec, C, rs, rsc, partial);
-    }
-    else if (grad_is_f32) bn_bwd_reduce_win2_kernel<true><<<grid, kRowThreads, smem, st>>>(yy, dA, scale, shift, mean, invstd, B, H, W, C, partial);
-    else bn_bwd_reduce_win2_kernel<false><<<grid, kRowThreads, smem, st>>>(yy, dA, scale, shift, mean, invstd, B, H, W, C, partial);
-    SED_LAUNCH_CHECK("bn_bwd_reduce_kernel");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p.kind == 1) {
+    if (grad_is_f32) bn_bwd_reduce_flat4_kernel<true><<<p.grid, kDynThreads, 0, st>>>(yy, dA, scale, shift, p.nvec, C, p.row_shift, p.row_scale, p.q, partial, sched);
+    else bn_bwd_reduce_flat4_kernel<false><<<p.grid, kDynThreads, 0, st>>>(yy, dA, scale, shift, p.nvec, C, p.row_shift, p.row_scale, p.q, partial, sched);
+    SED_LAUNCH_CHECK("bn_bwd_reduce_flat4_kernel");
     return 0;
   }
+  if (p.kind == 2) {
+    if (grad_is_f32) bn_bwd_reduce_win4_kernel<true><<<p.grid, kDynThreads, 0, st>>>(yy, dA, scale, shift, H, W, C, p.row_shift, p.q, partial, sched);
+    else bn_bwd_reduce_win4_kernel<false><<<p.grid, kDynThreads, 0, st>>>(yy, dA, scale, shift, H, W, C, p.row_shift, p.q, partial, sched);
+    SED_LAUNCH_CHECK("bn_bwd_reduce_win4_kernel");
+    return 0;
+  }
+  const int lanes = 256 / (C / 8);
+  const size_t smem = (size_t)lanes * 2 * C * sizeof(float);
   if (grad_is_f32)
-    bn_relu_pool_bwd_reduce_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(yy, dA, scale, shift, mean, invstd,
-                                                                                    B, H, W, C, ph, pw, partial);
+    bn_relu_pool_bwd_reduce_kernel<true><<<p.grid, 256, smem, st>>>(yy, dA, scale, shift, B, H, W, C, ph, pw, partial);
   else
-    bn_relu_pool_bwd_reduce_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>(yy, dA, scale, shift, mean, invstd,
-                                                                                     B, H, W, C, ph, pw, partial);
+    bn_relu_pool_bwd_reduce_kernel<false><<<p.grid, 256, smem, st>>>(yy, dA, scale, shift, B, H, W, C, ph, pw, partial);
   SED_LAUNCH_CHECK("bn_relu_pool_bwd_reduce_kernel");
   return 0;
 }
@@ -685,38 +808,35 @@ int sed_bn_bwd_finalize(const float* partial, int P, int C, double count, const 
 
 int sed_bn_relu_pool_bwd_apply(const void* y, const void* dA, int grad_is_f32, const float* scale, const float* shift,
                                const float* mean, const float* invstd, const float* coef, int B, int H, int W, int C,
-                               int ph, int pw, void* dy, sed_stream_t stream) {
-  SED_REQUIRE(y && dA && scale && shift && mean && invstd && coef && dy, "sed_bn_relu_pool_bwd_apply: null pointer");
+                               int ph, int pw, void* dy, int* sched, sed_stream_t stream) {
+  SED_REQUIRE(y && dA && scale && shift && mean && invstd && coef && dy && sched,
+              "sed_bn_relu_pool_bwd_apply: null pointer");
   SED_REQUIRE(C % 8 == 0, "sed_bn_relu_pool_bwd_apply: C must be a multiple of 8");
+  SED_REQUIRE(aligned(y, 16) && aligned(dA, 16) && aligned(dy, 16) && aligned(coef, 16),
+              "sed_bn_relu_pool_bwd_apply: pointers must be 16-byte aligned");
   if (B == 0) return 0;
-  const long long total = (long long)B * H * W * (C / 8);
-  const int grid = ew_grid(total, 256);
+  const BwdPlan p = make_bwd_plan(B, H, W, C, ph, pw);
   const __nv_bfloat16* yy = reinterpret_cast<const __nv_bfloat16*>(y);
   __nv_bfloat16* dd = reinterpret_cast<__nv_bfloat16*>(dy);
-  if (rows_path_ok(H, W, C, ph, pw) && (long long)B * H < (1LL << 31)) {
-    cudaStream_t st = (cudaStream_t)stream;
-    const long long nvec = (long long)B * H * W * (C / 8);
-    if (ph == 1) {
-      const int gf = sm_count() * 3;
-      const int rs = row_pool_shift(W, C, pw);
-      const float rsc = pw == 1 ? 1.0f : 1.0f / (float)pw;
-      if (grad_is_f32) bn_bwd_apply_flat_kernel<true><<<gf, kRowThreads, 0, st>>>(yy, dA, scale, shift, mean, invstd, coef, nvec, C, rs, rsc, dd);
-      else bn_bwd_apply_flat_kernel<false><<<gf, kRowThreads, 0, st>>>(yy, dA, scale, shift, mean, invstd, coef, nvec, C, rs, rsc, dd);
-    }
-    else {
-      const int g2 = rows_grid(B * (H / 2), 3);
-      if (grad_is_f32) bn_bwd_apply_win2_kernel<true><<<g2, kRowThreads, 0, st>>>(yy, dA, scale, shift, mean, invstd, coef, B, H, W, C, dd);
-      else bn_bwd_apply_win2_kernel<false><<<g2, kRowThreads, 0, st>>>(yy, dA, scale, shift, mean, invstd, coef, B, H, W, C, dd);
-    }
-    SED_LAUNCH_CHECK("bn_bwd_apply_kernel");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p.kind == 1) {
+    if (grad_is_f32) bn_bwd_apply_flat4_kernel<true><<<p.grid, kDynThreads, 0, st>>>(yy, dA, scale, shift, mean, invstd, coef, p.nvec, C, p.row_shift, p.row_scale, p.q, dd, sched);
+    else bn_bwd_apply_flat4_kernel<false><<<p.grid, kDynThreads, 0, st>>>(yy, dA, scale, shift, mean, invstd, coef, p.nvec, C, p.row_shift, p.row_scale, p.q, dd, sched);
+    SED_LAUNCH_CHECK("bn_bwd_apply_flat4_kernel");
     return 0;
   }
+  if (p.kind == 2) {
+    if (grad_is_f32) bn_bwd_apply_win4_kernel<true><<<p.grid, kDynThreads, 0, st>>>(yy, dA, scale, shift, mean, invstd, coef, B, H, W, C, p.row_shift, p.q, dd, sched);
+    else bn_bwd_apply_win4_kernel<false><<<p.grid, kDynThreads, 0, st>>>(yy, dA, scale, shift, mean, invstd, coef, B, H, W, C, p.row_shift, p.q, dd, sched);
+    SED_LAUNCH_CHECK("bn_bwd_apply_win4_kernel");
+    return 0;
+  }
+  const long long total = (long long)B * H * W * (C / 8);
+  const int grid = ew_grid(total, 256);
   if (grad_is_f32)
-    bn_relu_pool_bwd_apply_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(yy, dA, scale, shift, mean, invstd,
-                                                                                coef, B, H, W, C, ph, pw, dd);
+    bn_relu_pool_bwd_apply_kernel<true><<<grid, 256, 0, st>>>(yy, dA, scale, shift, mean, invstd, coef, B, H, W, C, ph, pw, dd);
   else
-    bn_relu_pool_bwd_apply_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(yy, dA, scale, shift, mean, invstd,
-                                                                                 coef, B, H, W, C, ph, pw, dd);
+    bn_relu_pool_bwd_apply_kernel<false><<<grid, 256, 0, st>>>(yy, dA, scale, shift, mean, invstd, coef, B, H, W, C, ph, pw, dd);
   SED_LAUNCH_CHECK("bn_relu_pool_bwd_apply_kernel");
   return 0;
 }

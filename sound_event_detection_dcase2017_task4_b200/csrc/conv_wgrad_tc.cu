@@ -475,6 +475,7 @@ struct KwPlan {
 };
 
 bool g_wgrad_cta2 = true;
+constexpr int kWgradSmemBudget = 208 * 1024;
 
 KwPlan make_kw_plan(int B, int H, int W, int Cin, int Cout) {
   KwPlan q;
@@ -489,7 +490,11 @@ KwPlan make_kw_plan(int B, int H, int W, int Cin, int Cout) {
   q.x_rows = 128 + 2 * W;
   q.cta2 = (g_wgrad_cta2 && Cout % 256 == 0 && q.kN == 128) ? 1 : 0;
   q.stage_bytes = 2 * kSlabBytes + (q.cta2 ? 1 : q.kN / 64) * q.x_rows * 128;
-  q.stages = (232448 - 2048) / q.stage_bytes;
+  // Shared-memory budget: 208 KB, not the full 227 KB.  The weight gradient of layer l runs on a side stream while the
+  // HBM-bound BatchNorm backward of layer l-1 runs on the main one (engine.trunk_backward); three of those 256-thread
+  // CTAs (5 KB each incl. the per-CTA reserve) must fit on the SM beside this CTA for the two to overlap.  Only the
+  // 64 -> 128 layer loses a stage (4 -> 3) to this.
+  q.stages = kWgradSmemBudget / q.stage_bytes;
   if (q.stages > 4) q.stages = 4;
   // One CTA per SM fits (shared memory), so the grid must not exceed ONE wave: with ceil(2 * SMs / items) splits
   // most layers launched 297-336 CTAs on 148 SMs, i.e. a nearly empty third wave (+50 % time).

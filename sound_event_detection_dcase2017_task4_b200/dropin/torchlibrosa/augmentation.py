@@ -12,6 +12,35 @@ from sound_event_detection_dcase2017_task4_b200 import ops as _ops
 from sound_event_detection_dcase2017_task4_b200 import specaug as _sa
 
 
+class _DropStripesFn(torch.autograd.Function):
+    """In-place stripe zeroing that autograd can see.  Upstream assigns ``e[:, bgn:bgn+d, :] = 0`` -- a tracked
+    in-place op, so the gradient is zeroed inside the stripes as well (the stripes sit between bn0 and the first
+    convolution: without this, bn0.weight / bn0.bias would collect gradient from masked positions)."""
+
+    @staticmethod
+    def forward(ctx, input, table, dim):
+        ctx.mark_dirty(input)
+        ctx.save_for_backward(table)
+        ctx.dim = dim
+        if dim == 2:
+            _ops.spec_augment_(input, table, None)
+        else:
+            _ops.spec_augment_(input, None, table)
+        return input
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (table,) = ctx.saved_tensors
+        g = grad_output.contiguous().clone()
+        if g.dtype != torch.float32:
+            raise RuntimeError('DropStripes backward: expected a float32 gradient')
+        if ctx.dim == 2:
+            _ops.spec_augment_(g, table, None)
+        else:
+            _ops.spec_augment_(g, None, table)
+        return g, None, None
+
+
 class DropStripes(nn.Module):
     def __init__(self, dim, drop_width, stripes_num):
         super().__init__()
@@ -29,6 +58,8 @@ class DropStripes(nn.Module):
         table = torch.from_numpy(stripes).to(input.device, non_blocking=True)
         if not (input.is_contiguous() and input.dtype == torch.float32):
             raise RuntimeError('DropStripes: expected a contiguous float32 tensor')
+        if torch.is_grad_enabled() and input.requires_grad:
+            return _DropStripesFn.apply(input, table, self.dim)
         if self.dim == 2:
             _ops.spec_augment_(input, table, None)
         else:

@@ -109,11 +109,11 @@ def trunk_forward(model, wave, lam, training, stripes=None, keep=None):
 
 
 _SIDE_STREAMS = {}
-# Side-stream schedule for the weight gradients (see trunk_backward).  Measured on B200 (tools/ab_step.py, batch 256):
-# 40.05 ms/step with it vs 39.8 ms without -- the one-wave BatchNorm-backward grids (3 CTAs/SM x 80 registers) leave
-# no register room for a co-resident tensor-core CTA, so the kernels serialise anyway.  Off until the BN kernels are
-# made co-residency friendly.
-OVERLAP_WGRAD = False
+# Side-stream schedule for the weight gradients (see trunk_backward).  Round 1 measured no gain (40.05 vs 39.8 ms/step)
+# because the kernels could not share an SM: the BatchNorm-backward grids were sized as one full wave of 3 CTAs/SM x 80
+# registers with up to 16 KB of shared memory, and the weight-gradient CTA took all 227 KB.  Round 2 rebuilt both sides
+# for co-residency (csrc/bnpool.cu "backward fast paths", csrc/conv_wgrad_tc.cu kWgradSmemBudget).
+OVERLAP_WGRAD = True
 # Fold the reduction pass of each BatchNorm backward into the epilogue of the data-gradient kernel that produces its dA
 # (sed_conv3x3_tc_dgrad_bnr).  Correct (tests/test_gpu_conv.py) but measured SLOWER on B200 at batch 256
 # (tools/ab_step.py: 42.1 vs 40.1 ms/step): the 8 epilogue warps cannot hide the HBM latency of the y reads that the
@@ -138,9 +138,10 @@ def trunk_backward(ctx, dfeat, grad_of, overlap_wgrad=None):
 
     Schedule: the critical chain BN-backward_l -> dgrad_l -> BN-backward_{l-1} ... stays on the current
     stream; the weight gradient of layer l only needs dY_l and the saved input, so it is enqueued on a side
-    stream behind an event.  The BN-backward kernels are HBM-bound and use no shared memory, the weight-gradient
-    kernels are tensor-pipe-bound and use all of it: co-resident on the same SMs they overlap instead of adding
-    up.  The current stream waits for the side stream before returning (the optimizer reads every gradient)."""
+    stream behind an event recorded right after BN-backward_l -- AFTER the data gradient has been enqueued, so
+    the chain's tensor kernel is ahead of it in issue order.  The BN-backward kernels are HBM-bound, the
+    weight-gradient kernels tensor-pipe-bound: co-resident on the same SMs they overlap instead of adding up.
+    The current stream waits for the side stream before returning (the optimizer reads every gradient)."""
     if overlap_wgrad is None:
         overlap_wgrad = OVERLAP_WGRAD
     dA = dfeat.contiguous().view(dfeat.shape[0], dfeat.shape[1], 1, dfeat.shape[2])
@@ -154,20 +155,14 @@ def trunk_backward(ctx, dfeat, grad_of, overlap_wgrad=None):
                                   grad_of(lc.bn.bias), gy_partial=gy_partial)
         gy_partial = None
         gw = grad_of(lc.conv.weight)
-        if gw is not None:
-            if overlap_wgrad:
-                ready = torch.cuda.Event()
-                ready.record(main)
-                side.wait_event(ready)
-                dy.record_stream(side)
-                lc.x_in.record_stream(side)
-                used_side = True
-            with torch.cuda.stream(side) if overlap_wgrad else _NullCtx():
-                if lc.is_c1:
-                    ops.conv_c1_wgrad(lc.x_in, dy, gw)
-                else:
-                    tcconv.conv3x3_wgrad(dy, lc.x_in, out=gw)
+        side_wgrad = overlap_wgrad and gw is not None and not lc.is_c1
+        if side_wgrad:
+            ready = torch.cuda.Event()
+            ready.record(main)
+        x_in = lc.x_in
         if lc.is_c1:
+            if gw is not None:
+                ops.conv_c1_wgrad(x_in, dy, gw)
             dA = ops.conv_c1_dgrad(dy, lc.conv.weight)                 # (B, T, M) fp32
         else:
             below = ctx.layers[li - 1]
@@ -177,6 +172,15 @@ def trunk_backward(ctx, dfeat, grad_of, overlap_wgrad=None):
                 dA, gy_partial = tcconv.conv3x3_dgrad_bnr(dy, lc.wd, cin, below.y, below.st, below.ph)
             else:
                 dA = tcconv.conv3x3(dy, lc.wd, cin)                    # bf16 NHWC
+            if side_wgrad:
+                side.wait_event(ready)
+                dy.record_stream(side)
+                x_in.record_stream(side)
+                used_side = True
+                with torch.cuda.stream(side):
+                    tcconv.conv3x3_wgrad(dy, x_in, out=gw)
+            elif gw is not None:
+                tcconv.conv3x3_wgrad(dy, x_in, out=gw)
         lc.y = lc.x_in = None
     g0w, g0b = grad_of(ctx.bn0.weight), grad_of(ctx.bn0.bias)
     if g0w is not None or g0b is not None:
@@ -185,14 +189,6 @@ def trunk_backward(ctx, dfeat, grad_of, overlap_wgrad=None):
         done = torch.cuda.Event()
         done.record(side)
         main.wait_event(done)
-
-
-class _NullCtx(object):
-    def __enter__(self):
-        return self
-
-    def __exit__(self, *a):
-        return False
 
 
 # ------------------------------------------------------------------ heads

@@ -146,6 +146,27 @@ class MultiHead(nn.Module):
 
 
 # ------------------------------------------------------------------ the fused model function
+def trainable_tensors(module):
+    """The tensors that carry gradient for ``module``, in ``module.parameters()`` order.
+
+    ``nn.DataParallel`` (pytorch/main.py:138) runs forward on *replicas* whose ``_parameters`` dicts are
+    empty: ``replicate()`` re-attaches every weight as a plain, non-leaf tensor attribute (the output of its
+    Broadcast autograd node) and records it in ``_former_parameters``.  ``replica.parameters()`` therefore
+    yields nothing, while ``replica.conv_block1.conv1.weight`` is the tensor the gradient must flow to.  This
+    walk reads whichever table the module instance really has, so the same code serves the original module
+    (leaf Parameters) and its replicas (broadcast copies)."""
+    out, seen = [], set()
+    for m in module.modules():
+        table = m._parameters
+        if getattr(m, '_is_replica', False) and getattr(m, '_former_parameters', None):
+            table = m._former_parameters
+        for p in table.values():
+            if p is not None and p.requires_grad and id(p) not in seen:
+                seen.add(id(p))
+                out.append(p)
+    return out
+
+
 class _SedFunction(torch.autograd.Function):
     """forward: waveform -> (clipwise, framewise, embedding) with libsedb200 kernels;
     backward: d clipwise -> gradients of every trainable parameter."""
@@ -167,7 +188,8 @@ class _SedFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dclip, _dframe, _demb):
         if ctx.saved is None:
-            raise RuntimeError('backward called on a forward that kept no activations (eval / no_grad)')
+            raise RuntimeError('backward through a forward that kept no activations: the B200 path saves them only '
+                               'in train() mode with grad enabled (eval-mode forwards are inference-only)')
         tctx, mctx, hctx = ctx.saved
         ctx.saved = None
         grads = {}
@@ -234,7 +256,7 @@ class _Cnn9(nn.Module):
         if not input.is_cuda:
             raise RuntimeError('%s: CUDA tensors required -- this package has no CPU path'
                                % type(self).__name__)
-        params = [p for p in self.parameters() if p.requires_grad]
+        params = trainable_tensors(self)      # not self.parameters(): empty on DataParallel replicas
         need_grad = self.training and torch.is_grad_enabled() and len(params) > 0
         clip, frame, emb = _SedFunction.apply(self, input, mixup_lambda, need_grad, *params)
         return {'framewise_output': frame, 'clipwise_output': clip, 'embedding': emb}

@@ -64,6 +64,19 @@ def bn_relu_pool_fwd(y, st, ph, pw, out_f32=False):
     return out
 
 
+_SCHED = {}
+
+
+def sched_words(t):
+    """Two zeroed int32 words per (device, stream) for the dynamically scheduled BatchNorm-backward kernels (ticket
+    counter + retired-CTA counter; the kernels leave them zero, see include/sed_b200.h)."""
+    key = (t.device.index, stream_of(t))
+    w = _SCHED.get(key)
+    if w is None:
+        w = _SCHED[key] = torch.zeros(2, dtype=torch.int32, device=t.device)
+    return w
+
+
 def bn_relu_pool_bwd(y, dA, st, bn, ph, pw, dgamma, dbeta, gy_partial=None):
     """Two-pass BN+ReLU+pool backward.  Writes bn parameter grads into dgamma/dbeta (fp32 (C,)
     tensors, may be None) and returns dY (bf16, same shape as y).
@@ -75,22 +88,20 @@ def bn_relu_pool_bwd(y, dA, st, bn, ph, pw, dgamma, dbeta, gy_partial=None):
     with _dev(y):
         coef = _empty((3, c), F32, y)
         s = stream_of(y)
+        sched = sched_words(y)
         if gy_partial is None:
-            P = _lib.lib().sed_bn_bwd_partials(c)
+            P = _lib.lib().sed_bn_bwd_partials(b, h, w, c, ph, pw)
             partial = _empty((P, 2, c), F32, y)
             call('sed_bn_relu_pool_bwd_reduce', y.data_ptr(), dA.data_ptr(), f32, st.scale.data_ptr(),
-                 st.shift.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(), b, h, w, c, ph, pw,
-                 partial.data_ptr(), s)
-            mean_for_gy = 0
+                 st.shift.data_ptr(), b, h, w, c, ph, pw, partial.data_ptr(), sched.data_ptr(), s)
         else:
             partial, P = gy_partial, gy_partial.shape[0]
-            mean_for_gy = st.mean.data_ptr()
         call('sed_bn_bwd_finalize', partial.data_ptr(), P, c, float(b * h * w), ptr(bn.weight),
-             st.invstd.data_ptr(), mean_for_gy, ptr(dgamma), ptr(dbeta), 0, coef.data_ptr(), s)
+             st.invstd.data_ptr(), st.mean.data_ptr(), ptr(dgamma), ptr(dbeta), 0, coef.data_ptr(), s)
         dy = _empty(y.shape, BF16, y)
         call('sed_bn_relu_pool_bwd_apply', y.data_ptr(), dA.data_ptr(), f32, st.scale.data_ptr(),
              st.shift.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(), coef.data_ptr(), b, h, w, c,
-             ph, pw, dy.data_ptr(), s)
+             ph, pw, dy.data_ptr(), sched.data_ptr(), s)
     return dy
 
 

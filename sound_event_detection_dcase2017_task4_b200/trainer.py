@@ -24,6 +24,30 @@ from . import ops
 from . import temporal
 
 
+# Run the step's critical chain on a high-priority stream: when the data gradient of layer l (chain) and the weight
+# gradient of layer l (side stream, engine.trunk_backward) become ready together, the block scheduler then dispatches the
+# chain's CTAs first.  The caller's current stream is joined before and after, so the step still looks synchronous to it.
+USE_PRIORITY_STREAM = False
+
+
+def shard_bounds(n_items, world_size, rank):
+    """Contiguous shard [lo, hi) of ``n_items`` raw clips for ``rank``: equal, EVEN-sized shards so that the mixup
+    pairs (2i, 2i+1) of pytorch_utils.do_mixup never straddle two ranks."""
+    if n_items % (2 * world_size) != 0:
+        raise ValueError('%d clips do not split into %d shards of whole mixup pairs' % (n_items, world_size))
+    per = n_items // world_size
+    return rank * per, (rank + 1) * per
+
+
+def exchange_gradients(flat_grad, world_size, group=None):
+    """The ONE collective of the step (replaces nn.DataParallel's reduce of per-replica gradients, main.py:138): every
+    rank has already scaled its loss gradient by 1/world_size, so the SUM over ranks is the gradient of the global-batch
+    mean loss.  Works on any backend torch.distributed offers (NCCL on the GPUs; gloo in the CPU tests)."""
+    if world_size > 1:
+        torch.distributed.all_reduce(flat_grad, op=torch.distributed.ReduceOp.SUM, group=group)
+    return flat_grad
+
+
 class FusedTrainer(object):
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, process_group=None, world_size=1):
         self.model = model
@@ -49,6 +73,7 @@ class FusedTrainer(object):
             self._grad[p] = self.flat_grad[off:off + n].view(p.shape)
             off += n
         self.step_count = 0
+        self._hp_stream = None
 
     def grad_of(self, p):
         if p is None or not p.requires_grad:
@@ -58,6 +83,23 @@ class FusedTrainer(object):
     def step(self, wave, target, lam):
         """wave (B2, L) fp32/int16, target (B2, K) fp32, lam (B2,) fp32 or None (all CUDA).
         Returns the rank-local loss as a 0-d CUDA tensor (no host sync here)."""
+        if USE_PRIORITY_STREAM:
+            cur = torch.cuda.current_stream(self.flat_param.device)
+            if self._hp_stream is None:
+                self._hp_stream = torch.cuda.Stream(device=self.flat_param.device, priority=-1)
+            hp = self._hp_stream
+            hp.wait_stream(cur)
+            with torch.cuda.stream(hp):
+                loss = self._step(wave, target, lam)
+                for t in (wave, target, lam):
+                    if t is not None:
+                        t.record_stream(hp)
+            cur.wait_stream(hp)
+            loss.record_stream(cur)
+            return loss
+        return self._step(wave, target, lam)
+
+    def _step(self, wave, target, lam):
         model = self.model
         with torch.no_grad():
             feat, tctx = engine.trunk_forward(model, wave, lam, True)
@@ -69,8 +111,7 @@ class FusedTrainer(object):
             dfeat = engine.head_backward(model, hctx, dprob, self.grad_of)
             dfeat = temporal.backward(model, mctx, dfeat, self.grad_of)
             engine.trunk_backward(tctx, dfeat, self.grad_of)
-            if self.world_size > 1:
-                torch.distributed.all_reduce(self.flat_grad, group=self.group)
+            exchange_gradients(self.flat_grad, self.world_size, self.group)
             self.step_count += 1
             ops.adam_amsgrad_(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq,
                               self.max_exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps,

@@ -13,6 +13,12 @@ CASES = [  # B, H, W, C, ph, pw, grad_f32
     (3, 50, 32, 128, 2, 2, False),
     (2, 25, 16, 256, 2, 2, False),     # odd H again
     (2, 12, 8, 512, 1, 8, True),       # block4.bn2 + mean over the 8 mel bins, fp32 features
+    (2, 50, 32, 128, 2, 2, True),      # stand-alone ConvBlock: fp32 gradient into a pooled layer
+    # large enough for many dynamically scheduled workers in both size tiers (csrc/bnpool.cu make_bwd_plan)
+    (6, 501, 64, 64, 1, 1, False),
+    (6, 501, 64, 64, 2, 2, False),
+    (24, 125, 8, 512, 1, 8, True),
+    (5, 33, 24, 72, 3, 2, False),      # nothing the fast paths take: generic kernels
 ]
 
 
@@ -74,3 +80,30 @@ def test_bn_eval_affine_matches_eval_mode():
     out = ops.bn_relu_pool_fwd(y, st, 2, 2, out_f32=True)
     ref = F.avg_pool2d(torch.relu(bn(y.float().permute(0, 3, 1, 2))), 2)
     assert (out.permute(0, 3, 1, 2) - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+
+
+def test_bn_backward_is_bit_reproducible_under_co_scheduling():
+    """The backward kernels take their work from an atomic ticket counter, yet every virtual worker owns a fixed range
+    and the finalize sums the per-worker rows in fixed order: the result may not depend on which CTA ran what -- not
+    even when another kernel occupies part of the machine."""
+    from sound_event_detection_dcase2017_task4_b200 import _lib, ops
+    B, H, W, C = 8, 501, 64, 64
+    y, bn, g = _setup(B, H, W, C, seed=3)
+    assert _lib.lib().sed_bn_bwd_partials(B, H, W, C, 2, 2) > 148
+    st = ops.bn_finalize(_partial(y), B * H * W, bn)
+    dA = torch.randn(B, H // 2, W // 2, C, generator=g).to(torch.bfloat16).cuda()
+    outs = []
+    side = torch.cuda.Stream()
+    junk = torch.randn(4096, 4096, device='cuda')
+    for rep in range(4):
+        dgamma, dbeta = torch.empty(C, device='cuda'), torch.empty(C, device='cuda')
+        if rep % 2:
+            with torch.cuda.stream(side):
+                for _ in range(4):
+                    junk @ junk                                  # competes for SMs while the BN kernels run
+        dy = ops.bn_relu_pool_bwd(y, dA, st, bn, 2, 2, dgamma, dbeta)
+        torch.cuda.synchronize()
+        outs.append((dy.clone(), dgamma.clone(), dbeta.clone()))
+    for o in outs[1:]:
+        assert all(torch.equal(a, b) for a, b in zip(o, outs[0]))
+    assert int(ops.sched_words(y).abs().sum()) == 0              # the ticket words are left zeroed

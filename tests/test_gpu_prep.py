@@ -74,3 +74,37 @@ def test_bn0_aug_mix_forward_backward(mixup):
     ops.bn0_bwd(dout[:, 0].contiguous().cuda(), lm, st, bn_d, t_d, f_d, lam_d, dg, db)
     assert torch.allclose(dg.cpu(), bn.weight.grad, rtol=1e-3, atol=1e-3)
     assert torch.allclose(db.cpu(), bn.bias.grad, rtol=1e-3, atol=1e-3)
+
+
+def test_spec_augment_module_masks_the_gradient_like_upstream():
+    """Seam A under autograd: upstream zeroes the stripes with a *tracked* in-place slice assignment,
+    so the gradient inside the stripes is zero too.  The drop-in must behave the same when its input is part of
+    an autograd graph (the bn0 output of the reference's own models.py:202-207)."""
+    from oracle import frontend as ofe
+    from sound_event_detection_dcase2017_task4_b200.dropin.torchlibrosa.augmentation import SpecAugmentation
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(5, 1, 101, 64, generator=g)
+    w = torch.randn(64, generator=g)
+    dout = torch.randn(5, 1, 101, 64, generator=g)
+    ref_mod = ofe.SpecAugmentation(time_drop_width=64, time_stripes_num=2, freq_drop_width=8, freq_stripes_num=2)
+    mine = SpecAugmentation(time_drop_width=64, time_stripes_num=2, freq_drop_width=8, freq_stripes_num=2)
+    ref_mod.train(); mine.train()
+    # reference: leaf -> affine (stands for bn0) -> in-place stripes
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    torch.manual_seed(5)
+    yr = ref_mod(xr * wr)
+    yr.backward(dout)
+    xd, wd = x.clone().cuda().requires_grad_(True), w.clone().cuda().requires_grad_(True)
+    torch.manual_seed(5)
+    yd = mine(xd * wd)
+    yd.backward(dout.cuda())
+    assert torch.equal(yd.detach().cpu() == 0, yr.detach() == 0)
+    assert torch.allclose(yd.detach().cpu(), yr.detach(), rtol=1e-6, atol=1e-6)
+    assert torch.equal(xd.grad.cpu() == 0, xr.grad == 0)                    # stripes carry no gradient
+    assert torch.allclose(xd.grad.cpu(), xr.grad, rtol=1e-6, atol=1e-6)
+    assert torch.allclose(wd.grad.cpu(), wr.grad, rtol=1e-4, atol=1e-4)
+    # no graph: plain in-place kernel, same values
+    torch.manual_seed(5)
+    with torch.no_grad():
+        y2 = mine((x * w).cuda())
+    assert torch.allclose(y2.cpu(), yr.detach(), rtol=1e-6, atol=1e-6)

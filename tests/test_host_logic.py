@@ -214,3 +214,78 @@ def test_abi_rejects_bad_arguments_before_touching_the_device():
     t.start()
     t.join()
     assert 'W=12' in msg() and 'W=12' not in seen[0]
+
+
+def test_product_mixup_matches_reference_golden(golden):
+    """Row a6: the product's own ``utilities.Mixup`` (utils/utilities.py:220-242) against lambdas minted from
+    the UNMODIFIED reference class (tests/golden/make_golden.py); bulk draws equal the per-pair draws."""
+    from sound_event_detection_dcase2017_task4_b200.utilities import Mixup, int16_to_float32
+    g, _ = golden
+    m = Mixup(mixup_alpha=1., random_seed=1234)
+    a = m.get_lambda(batch_size=32)
+    assert a.dtype == np.float64 and a[0] == 0.23538938957272115
+    assert np.array_equal(a, g['mixup_lambda_first32'])
+    assert np.array_equal(m.get_lambda(6), g['mixup_lambda_next6'])
+    # odd batch sizes round up to whole pairs, like the reference's range(0, n, 2) loop
+    ref = np.random.RandomState(7)
+    want = []
+    for _ in range(3):
+        lam = ref.beta(0.5, 0.5, 1)[0]
+        want += [lam, 1. - lam]
+    assert np.array_equal(Mixup(0.5, 7).get_lambda(5), np.array(want))
+    # in-place float32 fill == the cast of move_data_to_device (main.py:238)
+    buf = np.empty(32, dtype=np.float32)
+    Mixup(1., 1234).fill_lambda(buf)
+    assert np.array_equal(buf, g['mixup_lambda_first32'].astype(np.float32))
+    pcm = np.arange(-32768, 32768, dtype=np.int32).astype(np.int16)
+    assert np.array_equal(int16_to_float32(pcm), g['int16_to_float32_all'])
+
+
+def _emulated_replica(network):
+    """What torch.nn.parallel.replicate() builds for one device (torch 2.11), on CPU: modules shallow-copied by
+    ``_replicate_for_data_parallel`` (empty ``_parameters``), every weight re-attached as a plain NON-LEAF tensor
+    attribute and listed in ``_former_parameters``."""
+    from collections import OrderedDict
+    params = list(network.parameters())
+    copies = [p * 1 if p.requires_grad else p.detach().clone() for p in params]
+    index = {p: i for i, p in enumerate(params)}
+    modules = list(network.modules())
+    where = {m: i for i, m in enumerate(modules)}
+    reps = [m._replicate_for_data_parallel() for m in modules]
+    for r in reps:
+        r._former_parameters = OrderedDict()
+    for i, m in enumerate(modules):
+        for key, child in m._modules.items():
+            if child is None:
+                reps[i]._modules[key] = None
+            else:
+                setattr(reps[i], key, reps[where[child]])
+        for key, p in m._parameters.items():
+            if p is None:
+                reps[i]._parameters[key] = None
+            else:
+                setattr(reps[i], key, copies[index[p]])
+                reps[i]._former_parameters[key] = copies[index[p]]
+        for key, b in m._buffers.items():
+            setattr(reps[i], key, None if b is None else b.clone())
+    return reps[0], copies
+
+
+@pytest.mark.parametrize('name', ['Cnn_9layers_Gru_FrameAtt', 'Cnn_9layers_Transformer_FrameAvg'])
+def test_trainable_tensors_are_found_on_dataparallel_replicas(name):
+    """nn.DataParallel (main.py:138) runs forward on replicas whose parameters() is EMPTY.  The
+    model must still hand every weight that needs gradient to its autograd.Function -- otherwise loss.backward()
+    (main.py:257) has nothing to differentiate."""
+    from sound_event_detection_dcase2017_task4_b200 import models
+    torch.manual_seed(0)
+    net = getattr(models, name)(32000, 1024, 320, 64, 50, 14000, 17)
+    want = [p for p in net.parameters() if p.requires_grad]
+    assert [id(p) for p in models.trainable_tensors(net)] == [id(p) for p in want]
+    replica, copies = _emulated_replica(net)
+    assert list(replica.parameters()) == []                                    # the trap
+    got = models.trainable_tensors(replica)
+    expect = [c for c, p in zip(copies, net.parameters()) if p.requires_grad]
+    assert len(got) == len(want) and [id(t) for t in got] == [id(t) for t in expect]
+    assert all((not t.is_leaf) and t.requires_grad for t in got)
+    # the tensors the engine reads through attribute access are those same objects
+    assert replica.conv_block3.conv2.weight is got[[id(p) for p in want].index(id(net.conv_block3.conv2.weight))]
