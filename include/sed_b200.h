@@ -49,6 +49,8 @@ int sed_device_sm_count(int* out_sms);
  * Mel bank in CSR-by-mel form (built on the host from the module's frozen melW parameter):
  *   mel_lo[m]   first FFT bin with a non-zero tap,  mel_off[m]..mel_off[m+1] its taps in mel_w.
  * out = 10*log10(max(mel, amin)) - db_offset,  db_offset = 10*log10(max(amin, ref)).
+ * Limits of the fused kernels (the caller checks them; the tables live in device memory): n_mels <= 128 and
+ * sum over filters of ceil(taps / 16) <= 128 (the reference bank: 64 filters, 866 taps, 90 pieces).
  */
 int sed_logmel_f32(const float* wave, int n_clips, int n_samples, int hop,
                    const float* mel_w, const int* mel_lo, const int* mel_off, int n_mels,
@@ -128,9 +130,13 @@ int sed_bn_relu_pool_fwd(const void* y, const float* scale, const float* shift, 
  *   finalize -> dgamma, dbeta, coef[3][C] (pass the layer's batch mean as mean_for_gy);
  *   apply    -> dY = gamma*invstd * (g - mean(g) - xhat*mean(g*xhat))   (bf16).
  * The fast paths (pool 1x1, 1xW, 2x2; C/4 a power of two) are dynamically scheduled persistent kernels built to share
- * an SM with a weight-gradient CTA (<= 64 registers, 4 KB shared memory): `sched` points to TWO int32 words that are
- * zero before the call and zero again after it (one pair per stream that runs these kernels concurrently). */
-int sed_bn_bwd_partials(int B, int H, int W, int C, int ph, int pw);
+ * an SM with a weight-gradient CTA (<= 64 registers, 4 KB shared memory): `sched` points to
+ * sed_bn_bwd_sched_words() int32 words (work tickets + worker-group arrival counters) that are zero before the call
+ * and zero again after it (one block per stream that runs these kernels concurrently).  The reduce pass first writes
+ * one row per worker, then the last worker of every group of 16 folds the group into one of the first P rows. */
+int sed_bn_bwd_partials(int B, int H, int W, int C, int ph, int pw);        /* P: rows finalize reads = first rows of `partial` */
+int sed_bn_bwd_workspace_rows(int B, int H, int W, int C, int ph, int pw);  /* rows of [2][C] floats `partial` must hold */
+int sed_bn_bwd_sched_words(void);                                           /* int32 words behind `sched` */
 int sed_bn_relu_pool_bwd_reduce(const void* y, const void* dA, int grad_is_f32, const float* scale,
                                 const float* shift, int B, int H, int W, int C, int ph, int pw, float* partial,
                                 int* sched, sed_stream_t stream);

@@ -386,8 +386,8 @@ __device__ __forceinline__ void load_grad4(const void* dA, long long vec, float 
   else unpack4(ldg8(reinterpret_cast<const __nv_bfloat16*>(dA) + vec * 4), g);
 }
 
-// per-worker partial row: partial[w][0][c] = sum g, partial[w][1][c] = sum g*y.  Thread (pl, cv) holds 4 channels of
-// lane pl; the `lanes` = 256 / (C/4) lanes are summed in fixed order through a 4 KB scratch, one statistic at a time.
+// per-worker partial row: row[0][c] = sum g, row[1][c] = sum g*y.  Thread (pl, cv) holds 4 channels of lane pl; the
+// `lanes` = 256 / (C/4) lanes are summed in fixed order through a 4 KB scratch, one statistic at a time.
 __device__ __forceinline__ void dyn_write_partial(float* s_red, const float (&sg)[4], const float (&sgy)[4], int C, int cv,
                                                   int pl, int lanes, float* __restrict__ row) {
 #pragma unroll
@@ -403,13 +403,41 @@ __device__ __forceinline__ void dyn_write_partial(float* s_red, const float (&sg
     }
   }
 }
+// Second level, still inside the reduce kernel: workers are grouped by kGroup consecutive ids; the CTA that completes
+// the LAST worker of a group (whichever it is) adds the group's rows in worker order into one group row.  The sum is a
+// fixed-order sum of fixed operands, so it does not depend on the arrival order; the finalize kernel then reads
+// V / kGroup rows instead of V (with ~4000 workers it had become the longest link of the chain between two passes).
+// Layout of the workspace: group rows [0, G), worker rows [G, G + V).  gctr: G zeroed counters, re-zeroed here.
+constexpr int kGroup = 16;
+constexpr int kMaxGroups = 2046;      // sched workspace = 2 + kMaxGroups int32 words
+__device__ __forceinline__ void dyn_group_reduce(float* __restrict__ ws, int w, int V, int G, int C, int* gctr) {
+  __shared__ int s_last;
+  const int g = w / kGroup;
+  const int first = g * kGroup, count = min(kGroup, V - first);
+  __threadfence();                                   // this CTA's row is visible device-wide ...
+  __syncthreads();                                   // ... for every thread of it, before the arrival is counted
+  if (threadIdx.x == 0) {
+    const int arrived = atomicAdd(&gctr[g], 1);
+    s_last = arrived == count - 1;
+    if (s_last) atomicExch(&gctr[g], 0);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float* rows = ws + ((long long)G + first) * 2 * C;
+  for (int i = threadIdx.x; i < 2 * C; i += kDynThreads) {
+    float a = 0.f;
+    for (int r = 0; r < count; ++r) a += __ldcg(rows + (long long)r * 2 * C + i);
+    ws[(long long)g * 2 * C + i] = a;
+  }
+}
 
 // ---- un-pooled layers (and block 4's whole-row average): y, dA, dY are one flat stream of 8-byte vectors
 template <bool kGradF32>
 __global__ void __launch_bounds__(kDynThreads, 4)
 bn_bwd_reduce_flat4_kernel(const __nv_bfloat16* __restrict__ y, const void* __restrict__ dA_,
                            const float* __restrict__ scale, const float* __restrict__ shift, long long nvec, int C,
-                           int row_shift, float row_scale, DynPlan q, float* __restrict__ partial, int* sched) {
+                           int row_shift, float row_scale, DynPlan q, int G, float* __restrict__ partial, int* sched) {
   __shared__ float s_red[kDynThreads * 4];
   const int CV = C >> 2, cv = threadIdx.x & (CV - 1), pl = threadIdx.x / CV, lanes = kDynThreads / CV;
   float sc[4], sh[4];
@@ -436,7 +464,8 @@ bn_bwd_reduce_flat4_kernel(const __nv_bfloat16* __restrict__ y, const void* __re
         sgy[k] = fmaf(gk, x[k], sgy[k]);
       }
     }
-    dyn_write_partial(s_red, sg, sgy, C, cv, pl, lanes, partial + (long long)w * 2 * C);
+    dyn_write_partial(s_red, sg, sgy, C, cv, pl, lanes, partial + ((long long)G + w) * 2 * C);
+    dyn_group_reduce(partial, w, q.V, G, C, sched + 2);
   }
   dyn_retire(sched);
 }
@@ -497,7 +526,7 @@ template <bool kGradF32>
 __global__ void __launch_bounds__(kDynThreads, 4)
 bn_bwd_reduce_win4_kernel(const __nv_bfloat16* __restrict__ y, const void* __restrict__ dA_,
                           const float* __restrict__ scale, const float* __restrict__ shift, int H, int W, int C,
-                          int ov_shift, DynPlan q, float* __restrict__ partial, int* sched) {
+                          int ov_shift, DynPlan q, int G, float* __restrict__ partial, int* sched) {
   __shared__ float s_red[kDynThreads * 4];
   const int CV = C >> 2, Ho = H >> 1, cv = threadIdx.x & (CV - 1), pl = threadIdx.x / CV, lanes = kDynThreads / CV;
   const int cv_shift = __ffs(CV) - 1;
@@ -539,7 +568,8 @@ bn_bwd_reduce_win4_kernel(const __nv_bfloat16* __restrict__ y, const void* __res
         }
       }
     }
-    dyn_write_partial(s_red, sg, sgy, C, cv, pl, lanes, partial + (long long)w * 2 * C);
+    dyn_write_partial(s_red, sg, sgy, C, cv, pl, lanes, partial + ((long long)G + w) * 2 * C);
+    dyn_group_reduce(partial, w, q.V, G, C, sched + 2);
   }
   dyn_retire(sched);
 }
@@ -641,6 +671,7 @@ struct BwdPlan {
   long long nvec;    // flat: four-channel vectors
   DynPlan q;
   int grid;
+  int G;             // rows the finalize kernel reads (fast paths: worker groups; generic: one per CTA)
 };
 BwdPlan make_bwd_plan(int B, int H, int W, int C, int ph, int pw) {
   BwdPlan p;
@@ -664,6 +695,7 @@ BwdPlan make_bwd_plan(int B, int H, int W, int C, int ph, int pw) {
   } else {
     p.q.V = sm_count() * 3;          // rows of the partial workspace = grid of the generic reduce kernel
     p.grid = p.q.V;
+    p.G = p.q.V;
     return p;
   }
   // workers of ~768 KB of y (never fewer than 4 per SM, never more than 16 per SM in the first tier); the last quarter
@@ -680,8 +712,12 @@ BwdPlan make_bwd_plan(int B, int H, int W, int C, int ph, int pw) {
   const long long rest = n - v_big * big;
   const long long v_small = (rest + small - 1) / small;
   p.q.big = big; p.q.small = small; p.q.v_big = (int)v_big; p.q.V = (int)(v_big + v_small);
-  p.grid = sm_count() * 4;
+  // THREE CTAs per SM although four would fit on an empty SM (64 registers): four fill the register file, and a
+  // weight-gradient CTA that becomes ready while they run could not be placed until the whole (persistent) grid retires.
+  // With three, 16 K registers and > 210 KB of shared memory stay free on every SM at all times.
+  p.grid = sm_count() * 3;
   if (p.grid > p.q.V) p.grid = p.q.V;
+  p.G = (p.q.V + kGroup - 1) / kGroup;
   return p;
 }
 // log2(W * C/8) for the whole-row pooling form of the flat kernels, -1 for the un-pooled form
@@ -758,10 +794,16 @@ int sed_bn_relu_pool_fwd(const void* y, const float* scale, const float* shift, 
   return 0;
 }
 
-int sed_bn_bwd_partials(int B, int H, int W, int C, int ph, int pw) {   // rows of the partial workspace of the reduce pass
+int sed_bn_bwd_partials(int B, int H, int W, int C, int ph, int pw) {   // rows sed_bn_bwd_finalize reads (the FIRST rows)
   if (B < 1 || H < 1 || W < 1 || C < 8) return 0;
-  return make_bwd_plan(B, H, W, C, ph, pw).q.V;
+  return make_bwd_plan(B, H, W, C, ph, pw).G;
 }
+int sed_bn_bwd_workspace_rows(int B, int H, int W, int C, int ph, int pw) {   // rows of [2][C] floats the reduce pass needs
+  if (B < 1 || H < 1 || W < 1 || C < 8) return 0;
+  const BwdPlan p = make_bwd_plan(B, H, W, C, ph, pw);
+  return p.kind == 0 ? p.G : p.G + p.q.V;
+}
+int sed_bn_bwd_sched_words(void) { return 2 + kMaxGroups; }
 
 int sed_bn_relu_pool_bwd_reduce(const void* y, const void* dA, int grad_is_f32, const float* scale,
                                 const float* shift, int B, int H, int W, int C, int ph, int pw, float* partial,
@@ -772,17 +814,18 @@ int sed_bn_relu_pool_bwd_reduce(const void* y, const void* dA, int grad_is_f32, 
   SED_REQUIRE(aligned(y, 16) && aligned(dA, 16) && aligned(scale, 16) && aligned(shift, 16),
               "sed_bn_relu_pool_bwd_reduce: pointers must be 16-byte aligned");
   const BwdPlan p = make_bwd_plan(B, H, W, C, ph, pw);
+  SED_REQUIRE(p.kind == 0 || p.G <= kMaxGroups, "sed_bn_relu_pool_bwd_reduce: %d worker groups exceed the sched workspace", p.G);
   const __nv_bfloat16* yy = reinterpret_cast<const __nv_bfloat16*>(y);
   cudaStream_t st = (cudaStream_t)stream;
   if (p.kind == 1) {
-    if (grad_is_f32) bn_bwd_reduce_flat4_kernel<true><<<p.grid, kDynThreads, 0, st>>>(yy, dA, scale, shift, p.nvec, C, p.row_shift, p.row_scale, p.q, partial, sched);
-    else bn_bwd_reduce_flat4_kernel<false><<<p.grid, kDynThreads, 0, st>>>(yy, dA, scale, shift, p.nvec, C, p.row_shift, p.row_scale, p.q, partial, sched);
+    if (grad_is_f32) bn_bwd_reduce_flat4_kernel<true><<<p.grid, kDynThreads, 0, st>>>(yy, dA, scale, shift, p.nvec, C, p.row_shift, p.row_scale, p.q, p.G, partial, sched);
+    else bn_bwd_reduce_flat4_kernel<false><<<p.grid, kDynThreads, 0, st>>>(yy, dA, scale, shift, p.nvec, C, p.row_shift, p.row_scale, p.q, p.G, partial, sched);
     SED_LAUNCH_CHECK("bn_bwd_reduce_flat4_kernel");
     return 0;
   }
   if (p.kind == 2) {
-    if (grad_is_f32) bn_bwd_reduce_win4_kernel<true><<<p.grid, kDynThreads, 0, st>>>(yy, dA, scale, shift, H, W, C, p.row_shift, p.q, partial, sched);
-    else bn_bwd_reduce_win4_kernel<false><<<p.grid, kDynThreads, 0, st>>>(yy, dA, scale, shift, H, W, C, p.row_shift, p.q, partial, sched);
+    if (grad_is_f32) bn_bwd_reduce_win4_kernel<true><<<p.grid, kDynThreads, 0, st>>>(yy, dA, scale, shift, H, W, C, p.row_shift, p.q, p.G, partial, sched);
+    else bn_bwd_reduce_win4_kernel<false><<<p.grid, kDynThreads, 0, st>>>(yy, dA, scale, shift, H, W, C, p.row_shift, p.q, p.G, partial, sched);
     SED_LAUNCH_CHECK("bn_bwd_reduce_win4_kernel");
     return 0;
   }

@@ -25,6 +25,14 @@ constexpr int kThreads = 256;
 constexpr int kSlots = 4;              // frames in flight per CTA
 constexpr int kFramesPerChunk = 16;
 constexpr int kBuf = 8 * 72;           // one padded SoA plane of the 512-point work buffer
+// Mel projection schedule (built once per CTA in shared memory): every mel filter is cut into pieces of at most
+// kPieceTaps consecutive taps; piece p is owned by thread p % 64 of a frame slot.  The reference bank has 866 taps in
+// filters of 3..47 taps: one thread per filter made the 47-tap thread the critical path and every weight a scattered
+// 4-byte global load (ncu r01: 78 % excessive sectors, L1/TEX 80 % busy).  Pieces balance the slot (<= 22 taps per
+// thread instead of 47) and the weights are staged tap-major / piece-minor so a warp reads them without conflicts.
+constexpr int kPieceTaps = 16;
+constexpr int kMaxPieces = 128;
+constexpr int kMaxMels = 128;
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -107,7 +115,13 @@ logmel_kernel(const InT* __restrict__ wave, int n_clips, int n_samples, int hop,
               int chunks_per_clip, MelBank mel, float* __restrict__ out) {
   extern __shared__ __align__(16) float smem[];
   float* s_work = smem;                      // [kSlots][4][kBuf]  A.re A.im B.re B.im
-  float* s_span = s_work + kSlots * 4 * kBuf;  // [(FPC-1)*hop + 1024]
+  float* s_wil = s_work + kSlots * 4 * kBuf;   // [kPieceTaps][kMaxPieces] mel weights, tap-major (kPower: unused)
+  float* s_part = s_wil + kPieceTaps * kMaxPieces;                 // [kSlots][kMaxPieces] per-piece partial sums
+  int* s_pk0 = reinterpret_cast<int*>(s_part + kSlots * kMaxPieces);   // [kMaxPieces] first FFT bin of the piece
+  int* s_pn = s_pk0 + kMaxPieces;              // [kMaxPieces] taps in the piece
+  int* s_first = s_pn + kMaxPieces;            // [kMaxMels + 1] first piece of every mel filter
+  float* s_span = reinterpret_cast<float*>(s_first + kMaxMels + 4);    // [(FPC-1)*hop + 1024], 16-byte aligned
+  __shared__ int s_npieces;
 
   const int tid = threadIdx.x;
   const int slot = tid >> 6;
@@ -136,6 +150,32 @@ logmel_kernel(const InT* __restrict__ wave, int n_clips, int n_samples, int hop,
 #pragma unroll
     for (int sI = 0; sI < 4; ++sI) tws[sI] = twiddle(j + 64 * sI, kNfft);
   }
+
+  if (!kPower) {
+    if (tid == 0) {
+      int np = 0;
+      for (int m = 0; m < mel.n_mels; ++m) {
+        s_first[m] = np;
+        const int lo = mel.lo[m], o0 = mel.off[m], n = mel.off[m + 1] - o0;
+        for (int c = 0; c < n; c += kPieceTaps) {
+          s_pk0[np] = lo + c;
+          s_pn[np] = min(kPieceTaps, n - c);
+          ++np;
+        }
+      }
+      s_first[mel.n_mels] = np;
+      s_npieces = np;
+    }
+    for (int i = tid; i < kPieceTaps * kMaxPieces; i += kThreads) s_wil[i] = 0.f;
+    __syncthreads();
+    // weights: tap t of filter m belongs to piece s_first[m] + (t - off[m]) / kPieceTaps, position (t - off[m]) % kPieceTaps
+    for (int m = tid; m < mel.n_mels; m += kThreads) {
+      const int o0 = mel.off[m], n = mel.off[m + 1] - o0, p0 = s_first[m];
+      for (int i = 0; i < n; ++i) s_wil[(i % kPieceTaps) * kMaxPieces + p0 + i / kPieceTaps] = mel.w[o0 + i];
+    }
+    __syncthreads();
+  }
+  const int n_pieces = kPower ? 0 : s_npieces;
 
   const long long total_items = (long long)n_clips * chunks_per_clip;
   for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -255,12 +295,28 @@ logmel_kernel(const InT* __restrict__ wave, int n_clips, int n_samples, int hop,
         if (kPower) {
           float* dst = out + frame * kBins;
           for (int k = j; k < kBins; k += 64) dst[k] = P[k];
-        } else {
+        }
+      }
+      if (!kPower) {
+        // mel projection in two balanced steps: per-piece partial sums, then one thread per filter adds its pieces
+        // in fixed order, converts to dB and stores (64 consecutive floats per frame).
+        float* part = s_part + slot * kMaxPieces;
+        if (live) {
+          for (int p = j; p < n_pieces; p += 64) {
+            const int k0 = s_pk0[p], n = s_pn[p];
+            float acc = 0.f;
+#pragma unroll 4
+            for (int i = 0; i < n; ++i) acc = fmaf(s_wil[i * kMaxPieces + p], P[k0 + i], acc);
+            part[p] = acc;
+          }
+        }
+        slot_barrier(slot);
+        if (live) {
+          const long long frame = (long long)clip * n_frames + frame0 + f;
           float* dst = out + frame * mel.n_mels;
           for (int m = j; m < mel.n_mels; m += 64) {
-            const int lo = __ldg(mel.lo + m), o0 = __ldg(mel.off + m), o1 = __ldg(mel.off + m + 1);
             float acc = 0.f;
-            for (int t = o0; t < o1; ++t) acc = fmaf(__ldg(mel.w + t), P[lo + (t - o0)], acc);
+            for (int p = s_first[m]; p < s_first[m + 1]; ++p) acc += part[p];
             dst[m] = 10.0f * log10f(fmaxf(acc, mel.amin)) - mel.db_offset;
           }
         }
@@ -281,7 +337,9 @@ int launch_logmel(const InT* wave, int n_clips, int n_samples, int hop, MelBank 
   SED_REQUIRE(wave && out, "%s: null pointer", name);
   const int n_frames = n_samples / hop + 1;
   const int chunks = ceil_div(n_frames, kFramesPerChunk);
-  const size_t smem = sizeof(float) * (size_t)(kSlots * 4 * kBuf + (kFramesPerChunk - 1) * hop + kNfft);
+  SED_REQUIRE(kPower || mel.n_mels <= kMaxMels, "%s: at most %d mel filters (got %d)", name, kMaxMels, mel.n_mels);
+  const size_t smem = sizeof(float) * (size_t)(kSlots * 4 * kBuf + kPieceTaps * kMaxPieces + kSlots * kMaxPieces +
+                                               2 * kMaxPieces + kMaxMels + 4 + (kFramesPerChunk - 1) * hop + kNfft);
   auto kern = logmel_kernel<InT, kPower>;
   static thread_local int configured_dev = -1;   // attribute is per (function, device)
   int dev = 0;

@@ -191,19 +191,37 @@ def collate_fn(list_data_dict):
 
 class TrainBatcher(object):
     """The fast path the fused trainer uses instead of DataLoader(dataset, batch_sampler, collate_fn): the same index
-    stream as ``TrainSampler``, batches gathered from the memmap as int16 into (optionally pinned) buffers."""
+    stream as ``TrainSampler``, batches gathered from the memmap as int16 into (optionally pinned) buffers.
 
-    def __init__(self, store_path, batch_size, random_seed=1234, pinned=False):
+    ``pinned=True`` keeps ``slots`` independent sets of pinned buffers and fills them round-robin: batch i lives in
+    set i % slots (``batch['slot']``), so an asynchronous host->device copy of batch i (feed.DeviceFeed.submit) is not
+    overwritten by the gather of batch i+1.  Before set k is refilled, ``before_refill(k)`` is called if given -- pass
+    ``DeviceFeed.wait_copied`` so that the refill waits for the copy that last read that set."""
+
+    def __init__(self, store_path, batch_size, random_seed=1234, pinned=False, slots=2, before_refill=None):
         self.sampler = TrainSampler(store_path, batch_size, random_seed)
         self.store = _store(store_path)
         self.buffers = None
+        self.before_refill = before_refill
         if pinned:
             import torch
             s = self.store
-            self._pinned = {'waveform': torch.empty((batch_size, s.samples), dtype=torch.int16).pin_memory(),
-                            'target': torch.empty((batch_size, s.classes_num), dtype=torch.float32).pin_memory()}
-            self.buffers = {k: v.numpy() for k, v in self._pinned.items()}
+            self._pinned = [{'waveform': torch.empty((batch_size, s.samples), dtype=torch.int16).pin_memory(),
+                             'target': torch.empty((batch_size, s.classes_num), dtype=torch.float32).pin_memory()}
+                            for _ in range(max(1, slots))]
+            self.buffers = [{k: v.numpy() for k, v in d.items()} for d in self._pinned]
 
     def __iter__(self):
+        i = 0
         while True:
-            yield self.store.gather(self.sampler.next_indexes(), out=self.buffers)
+            if self.buffers is None:
+                yield self.store.gather(self.sampler.next_indexes())
+            else:
+                slot = i % len(self.buffers)
+                if self.before_refill is not None:
+                    self.before_refill(slot)
+                batch = self.store.gather(self.sampler.next_indexes(), out=self.buffers[slot])
+                batch['slot'] = slot
+                batch['pinned'] = self._pinned[slot]
+                yield batch
+            i += 1

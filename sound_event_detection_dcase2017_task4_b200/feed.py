@@ -35,6 +35,12 @@ class DeviceFeed(object):
                 ev.record(self.stream)
                 self.ready[slot] = ev
 
+    def wait_copied(self, slot):
+        """Block the HOST until the last copy submitted into ``slot`` has finished reading its pinned source (call
+        before overwriting that host buffer; data_generator.TrainBatcher(before_refill=feed.wait_copied))."""
+        if slot < len(self.ready) and self.ready[slot] is not None:
+            self.ready[slot].synchronize()
+
     def acquire(self, slot):
         """Device tensors of ``slot``; the current stream waits for the copy."""
         torch.cuda.current_stream(self.device).wait_event(self.ready[slot])

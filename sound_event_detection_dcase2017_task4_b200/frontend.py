@@ -76,6 +76,12 @@ class MelBankCSR(object):
             taps.append(run)
             off[m + 1] = off[m] + len(run)
         flat = np.concatenate(taps) if taps else np.zeros(1, dtype=np.float32)
+        # limits of the fused kernel's shared-memory projection schedule (csrc/logmel.cu: kMaxMels, kMaxPieces,
+        # pieces of <= 16 consecutive taps); the reference bank needs 64 filters / 90 pieces
+        pieces = int(sum((int(off[m + 1] - off[m]) + 15) // 16 for m in range(n_mels)))
+        if n_mels > 128 or pieces > 128:
+            raise NotImplementedError('mel bank too large for the fused log-mel kernel: %d filters / %d 16-tap pieces '
+                                      '(limits 128 / 128)' % (n_mels, pieces))
         dev = melW.device
         self.n_bins, self.n_mels = n_bins, n_mels
         self.w = torch.from_numpy(np.ascontiguousarray(flat, dtype=np.float32)).to(dev)

@@ -68,12 +68,12 @@ _SCHED = {}
 
 
 def sched_words(t):
-    """Two zeroed int32 words per (device, stream) for the dynamically scheduled BatchNorm-backward kernels (ticket
-    counter + retired-CTA counter; the kernels leave them zero, see include/sed_b200.h)."""
+    """Zeroed int32 scheduling words per (device, stream) for the dynamically scheduled BatchNorm-backward kernels
+    (work tickets + worker-group arrival counters; the kernels leave them zero, see include/sed_b200.h)."""
     key = (t.device.index, stream_of(t))
     w = _SCHED.get(key)
     if w is None:
-        w = _SCHED[key] = torch.zeros(2, dtype=torch.int32, device=t.device)
+        w = _SCHED[key] = torch.zeros(_lib.lib().sed_bn_bwd_sched_words(), dtype=torch.int32, device=t.device)
     return w
 
 
@@ -91,7 +91,7 @@ def bn_relu_pool_bwd(y, dA, st, bn, ph, pw, dgamma, dbeta, gy_partial=None):
         sched = sched_words(y)
         if gy_partial is None:
             P = _lib.lib().sed_bn_bwd_partials(b, h, w, c, ph, pw)
-            partial = _empty((P, 2, c), F32, y)
+            partial = _empty((_lib.lib().sed_bn_bwd_workspace_rows(b, h, w, c, ph, pw), 2, c), F32, y)
             call('sed_bn_relu_pool_bwd_reduce', y.data_ptr(), dA.data_ptr(), f32, st.scale.data_ptr(),
                  st.shift.data_ptr(), b, h, w, c, ph, pw, partial.data_ptr(), sched.data_ptr(), s)
         else:

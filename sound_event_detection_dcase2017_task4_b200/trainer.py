@@ -24,12 +24,6 @@ from . import ops
 from . import temporal
 
 
-# Run the step's critical chain on a high-priority stream: when the data gradient of layer l (chain) and the weight
-# gradient of layer l (side stream, engine.trunk_backward) become ready together, the block scheduler then dispatches the
-# chain's CTAs first.  The caller's current stream is joined before and after, so the step still looks synchronous to it.
-USE_PRIORITY_STREAM = False
-
-
 def shard_bounds(n_items, world_size, rank):
     """Contiguous shard [lo, hi) of ``n_items`` raw clips for ``rank``: equal, EVEN-sized shards so that the mixup
     pairs (2i, 2i+1) of pytorch_utils.do_mixup never straddle two ranks."""
@@ -73,7 +67,6 @@ class FusedTrainer(object):
             self._grad[p] = self.flat_grad[off:off + n].view(p.shape)
             off += n
         self.step_count = 0
-        self._hp_stream = None
 
     def grad_of(self, p):
         if p is None or not p.requires_grad:
@@ -83,23 +76,6 @@ class FusedTrainer(object):
     def step(self, wave, target, lam):
         """wave (B2, L) fp32/int16, target (B2, K) fp32, lam (B2,) fp32 or None (all CUDA).
         Returns the rank-local loss as a 0-d CUDA tensor (no host sync here)."""
-        if USE_PRIORITY_STREAM:
-            cur = torch.cuda.current_stream(self.flat_param.device)
-            if self._hp_stream is None:
-                self._hp_stream = torch.cuda.Stream(device=self.flat_param.device, priority=-1)
-            hp = self._hp_stream
-            hp.wait_stream(cur)
-            with torch.cuda.stream(hp):
-                loss = self._step(wave, target, lam)
-                for t in (wave, target, lam):
-                    if t is not None:
-                        t.record_stream(hp)
-            cur.wait_stream(hp)
-            loss.record_stream(cur)
-            return loss
-        return self._step(wave, target, lam)
-
-    def _step(self, wave, target, lam):
         model = self.model
         with torch.no_grad():
             feat, tctx = engine.trunk_forward(model, wave, lam, True)
