@@ -1,6 +1,7 @@
 """bench.py -- the hot path's headline metric on N B200s of one node.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--model NAME] [--batch B] [--workload train|logmel|eval]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
@@ -20,6 +21,13 @@ read back to the host every step.  ``roofline``: the 3x3 tensor-core convolution
 peak.  ``cpu_baseline`` / ``--impl reference``: the CPU oracle (oracle/sed.py, a restatement of
 the reference's PyTorch modules pinned to the unmodified reference by tests/golden) timed on
 this box's host cores on a bounded sample of the same workload.
+
+Other BASELINE.json configurations (the default invocation above is unchanged by these switches):
+  --model Cnn_9layers_FrameAvg                            config 2 (batch_size 256 + mixup, 1 GPU)
+  --model Cnn_9layers_Transformer_FrameAvg --batch 128    config 4
+  --workload logmel                                       config 5's headline point: log-mel only, 512 raw 10 s clips per
+                                                          GPU per launch, Mframes/s against the HBM roofline (replicas)
+  --workload eval                                         row f3: pytorch_utils.forward over host int16 batches, clips/s
 """
 import argparse
 import json
@@ -37,8 +45,34 @@ if ROOT not in sys.path:
 MODEL = 'Cnn_9layers_Gru_FrameAtt'
 CTOR = (32000, 1024, 320, 64, 50, 14000, 17)
 CLIP_SAMPLES = 320000
-METRIC = '10s-clips/sec train %s (raw clips consumed, batch_size 256 + mixup per GPU)' % MODEL
 UNIT = 'clips/s'
+
+
+def metric_name(model):
+    # shared by both arms: the per-arm batch size is a property of the run (config.batch_size), not of the metric
+    return '10s-clips/sec train %s (raw 10 s clips consumed per second, mixup)' % model
+
+def train_config(model, bs, world):
+    """`config` of the train workload -- identical in both arms (the reference arm times a bounded SAMPLE of it and
+    says so in cpu_baseline.sample)."""
+    b2 = 2 * bs
+    return {'workload': '%s train step (log-mel, bn0, SpecAugment, mixup, 4 ConvBlocks, %s, clip_bce, backward, '
+                        'Adam-amsgrad), batch_size %d + mixup = %d raw 32 kHz x 10 s clips per GPU per step'
+                        % (model, head_words(model), bs, b2),
+            'batch_size_per_gpu': bs, 'raw_clips_per_gpu_per_step': b2,
+            'parallelism': 'dp%d, one NCCL all-reduce of the flat fp32 gradient per step' % world,
+            'precision': 'bf16 tensor-core operands / activations, fp32 accumulation, fp32 front-end, '
+                         'BN statistics, GRU, heads, loss, optimizer',
+            'l2': 'inputs larger than L2 (waveforms %.0f MB per step, activations > 10 GB)'
+                  % (b2 * CLIP_SAMPLES * 4 / 1e6)}
+
+
+def head_words(model):
+    temporal = 'biGRU' if '_Gru_' in model else ('multi-head self-attention' if '_Transformer_' in model else 'no temporal module')
+    pool = {'Att': 'attention head', 'Avg': 'fc + mean-over-time head', 'Max': 'fc + max-over-time head'}[model[-3:]]
+    return '%s, %s' % (temporal, pool)
+
+
 # 3x3 conv FLOPs per training sample of one pass (SURVEY.md section 8d): layers with Cin >= 64
 CONV_TC_LAYERS = [(1001, 64, 64, 64), (500, 32, 64, 128), (500, 32, 128, 128), (250, 16, 128, 256),
                   (250, 16, 256, 256), (125, 8, 256, 512), (125, 8, 512, 512)]
@@ -52,6 +86,15 @@ def measured_peaks():
         return {'hbm_gbs': p['hbm_gbs'], 'bf16_burst': p['bf16_tflops'],
                 'bf16_sustained': p.get('bf16_tflops_sustained', p['bf16_tflops']), 'source': 'measured'}
     return {'hbm_gbs': 6650.0, 'bf16_burst': 1590.0, 'bf16_sustained': 1400.0, 'source': 'fallback'}
+
+
+def profile_value(name, key='dram_bytes_per_launch_avg'):
+    """A per-launch figure from a committed ncu summary under profiles/ (None if absent)."""
+    path = os.path.join(ROOT, 'profiles', name)
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f).get(key)
 
 
 def conv_traffic():
@@ -125,7 +168,7 @@ def synthetic_rank_batch(b2, rank):
 
 
 # ----------------------------------------------------------------------------- reference / CPU arm
-def cpu_oracle_run(steps, warmup, batch_size, threads):
+def cpu_oracle_run(steps, warmup, batch_size, threads, model_name=MODEL):
     """Times the CPU oracle's train step (same model, mixup, Adam-amsgrad) on a bounded sample:
     ``batch_size`` training samples = 2*batch_size raw clips per step.  Returns clips/s."""
     import numpy as np
@@ -133,7 +176,7 @@ def cpu_oracle_run(steps, warmup, batch_size, threads):
     from oracle import sed
     torch.set_num_threads(threads)
     torch.manual_seed(0)
-    model = sed.build(MODEL)
+    model = sed.build(model_name)
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.,
                            amsgrad=True)
     b2 = 2 * batch_size
@@ -153,26 +196,224 @@ def cpu_oracle_run(steps, warmup, batch_size, threads):
 
 
 def run_reference(args):
+    """The reference arm: the CPU restatement of the reference's own modules (oracle/sed.py; the reference cannot be
+    installed -- pure Python + an un-vendored dependency) on the box's host cores, same metric and
+    config as our arm, each step a bounded sample (batch_size 8 + mixup = 16 raw clips instead of 512)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return 0
+    if args.workload != 'train':
+        print(json.dumps({'impl': 'reference', 'unavailable': 'the reference arm covers the train workload only'}), flush=True)
+        return 0
     threads = os.cpu_count() or 1
     bs = 8 if args.steps <= 24 else (4 if args.steps <= 60 else 2)
-    value, sec = cpu_oracle_run(args.steps, args.warmup, bs, threads)
+    value, sec = cpu_oracle_run(args.steps, args.warmup, bs, threads, args.model)
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'impl': 'reference', 'metric': metric_name(args.model), 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': '%s train step (fwd + clip_bce + bwd + Adam-amsgrad), mixup, 32 kHz x 10 s clips' % MODEL,
-                   'batch_size': bs, 'raw_clips_per_step': 2 * bs},
+        'config': train_config(args.model, args.batch, args.gpus),
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                          'sample': 'CPU oracle (oracle/sed.py, PyTorch CPU fp32 restatement pinned to the '
-                                   'unmodified reference), %d steps of batch_size %d + mixup = %d raw clips/step'
-                                   % (args.steps, bs, 2 * bs)},
+                                   'unmodified reference), %d timed steps of batch_size %d + mixup = %d raw clips/step '
+                                   '(a bounded sample of the %d-clip step), fp32'
+                                   % (args.steps, bs, 2 * bs, 2 * args.batch)},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------- log-mel-only workload (config 5)
+def _dist_setup():
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py: no CUDA device; the product path has no CPU fallback '
+                           '(use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    return world, rank, local_rank, dev
+
+
+def _timed_region(fn, steps, world, dev):
+    """EXACTLY `steps` calls between barrier + synchronize pairs; device time, max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def run_logmel(args):
+    """BASELINE.json config 5, headline point of the sweep (tools/logmel_sweep.py walks the rest): Spectrogram +
+    LogmelFilterBank (models.py:199-200) alone on 512 raw 32 kHz x 10 s clips per GPU per launch.  The path shards by
+    clip with no exchange: N GPUs = N replicas on their own clips (`scaling: weak`, no collective)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    world, rank, local_rank, dev = _dist_setup()
+    from sound_event_detection_dcase2017_task4_b200 import _lib, frontend as fe
+    _lib.lib()
+    b2 = 2 * args.batch
+    bank = fe.MelBankCSR(torch.from_numpy(fe.mel_weight_matrix(*[CTOR[i] for i in (0, 1, 3, 4, 5)])).to(dev))
+    pcm, _ = synthetic_rank_batch(b2, rank)
+    pcm_host = torch.from_numpy(pcm).pin_memory()
+    wave_host = torch.from_numpy((pcm / np.float32(32767.)).astype(np.float32)).pin_memory()
+    wave_dev = wave_host.to(dev)
+    frames_per_clip = CLIP_SAMPLES // CTOR[2] + 1
+    out = torch.empty((b2, 1, frames_per_clip, 64), device=dev)
+    out_host = torch.empty((b2, 1, frames_per_clip, 64)).pin_memory()
+    stage = torch.empty_like(wave_dev)
+    stage16 = torch.empty((b2, CLIP_SAMPLES), dtype=torch.int16, device=dev)
+
+    def resident():
+        fe.logmel(wave_dev, CTOR[2], bank, out=out)
+
+    def e2e():
+        stage.copy_(wave_host, non_blocking=True)
+        fe.logmel(stage, CTOR[2], bank, out=out)
+        out_host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def e2e_i16():
+        stage16.copy_(pcm_host, non_blocking=True)
+        fe.logmel(stage16, CTOR[2], bank, out=out)
+        out_host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        resident()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    n0 = _lib.launch_count()
+    ms = _timed_region(resident, args.steps, world, dev)
+    launches = _lib.launch_count() - n0
+    clock_info = clocks.stop() if rank == 0 else None
+    for _ in range(2):
+        e2e()
+    ms_e2e = _timed_region(e2e, args.steps, world, dev)
+    for _ in range(2):
+        e2e_i16()
+    ms_e2e16 = _timed_region(e2e_i16, args.steps, world, dev)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import frontend as ofe
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        spec = ofe.Spectrogram(n_fft=1024, hop_length=320, win_length=1024, window='hann', center=True,
+                               pad_mode='reflect', freeze_parameters=True)
+        lmel = ofe.LogmelFilterBank(sr=32000, n_fft=1024, n_mels=64, fmin=50, fmax=14000, ref=1.0, amin=1e-10,
+                                    top_db=None, freeze_parameters=True)
+        x = wave_host[:8].clone()
+        with torch.no_grad():
+            lmel(spec(x))
+            t0 = time.perf_counter()
+            reps = 0
+            while time.perf_counter() - t0 < 10.0:
+                lmel(spec(x))
+                reps += 1
+            sec = (time.perf_counter() - t0) / reps
+        cpu = {'value': 8 * frames_per_clip / sec / 1e6, 'unit': 'Mframes/s', 'cores': threads, 'kind': 'port',
+               'sample': 'oracle/frontend.py Spectrogram + LogmelFilterBank (the restated torchlibrosa 0.0.4 conv1d DFT '
+                         '+ dense mel matmul), batch of 8 x 10 s clips, %d repeats, %.1f ms each' % (reps, sec * 1e3)}
+    if rank == 0:
+        peaks = measured_peaks()
+        frames = b2 * frames_per_clip * world * args.steps
+        bytes_per_launch = b2 * (CLIP_SAMPLES * 4 + frames_per_clip * 64 * 4)
+        ms_launch = ms / args.steps
+        achieved = bytes_per_launch / ms_launch / 1e6
+        line = {
+            'metric': 'logmel Mframes/s (Spectrogram + LogmelFilterBank, 32 kHz x 10 s clips)', 'value': frames / ms / 1e3,
+            'unit': 'Mframes/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': ms_launch, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic',
+            'config': {'workload': 'log-mel only (BASELINE config 5, sweep point 10 s x %d clips per GPU): framed rFFT-1024, '
+                                   'power, sparse mel, 10 log10; fp32 waveform in, fp32 (T, 64) out' % b2,
+                       'clips_per_gpu_per_step': b2, 'parallelism': 'replicas x%d, no collective' % world,
+                       'l2': 'inputs larger than L2 (%.0f MB of waveforms per launch)' % (b2 * CLIP_SAMPLES * 4 / 1e6)},
+            'e2e': {'value': frames / ms_e2e / 1e3, 'unit': 'Mframes/s', 'ms_per_step': ms_e2e / args.steps,
+                    'h2d_bytes_per_step': int(wave_host.numel() * 4), 'd2h_bytes_per_step': int(out_host.numel() * 4),
+                    'input': 'fp32 waveforms in pinned host memory -> device -> kernel -> pinned host log-mel'},
+            'e2e_int16': {'value': frames / ms_e2e16 / 1e3, 'unit': 'Mframes/s', 'ms_per_step': ms_e2e16 / args.steps,
+                          'h2d_bytes_per_step': int(pcm_host.numel() * 2), 'd2h_bytes_per_step': int(out_host.numel() * 4)},
+            'gpu_launches': launches, 'clocks': clock_info,
+            'roofline': {'kernel': 'logmel_kernel<float> (sed_logmel_f32)', 'bound': 'hbm', 'achieved': round(achieved, 1),
+                         'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': round(achieved / peaks['hbm_gbs'], 4),
+                         'peak_source': peaks['source'] + ' hbm_gbs', 'bytes_per_launch': bytes_per_launch,
+                         'avg_launch_ms': round(ms_launch, 4), 'traffic': profile_value('logmel_traffic.json')},
+            'cpu_baseline': cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def run_eval(args):
+    """Row f3: the inference loop (pytorch_utils.forward, /root/reference/pytorch/pytorch_utils.py:25-77) over host
+    batches of int16 PCM, eval-mode model, outputs drained to host numpy arrays -- 10 s clips per second."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    world, rank, local_rank, dev = _dist_setup()
+    from sound_event_detection_dcase2017_task4_b200 import _lib, models, pytorch_utils
+    _lib.lib()
+    bs = args.batch
+    torch.manual_seed(0)
+    model = getattr(models, args.model)(*CTOR).to(dev)
+    pcm, target = synthetic_rank_batch(bs, rank)
+    names = np.array(['Y%05d.wav' % i for i in range(bs)])
+    batches = [{'audio_name': names, 'waveform': pcm, 'target': target}] * 4
+
+    def loop():
+        out = pytorch_utils.forward(model, batches, return_target=True)
+        assert out['framewise_output'].shape == (4 * bs, 1000, 17)
+
+    for _ in range(max(2, min(args.warmup, 3))):
+        loop()
+    n0 = _lib.launch_count()
+    ms = _timed_region(loop, args.steps, world, dev)
+    launches = _lib.launch_count() - n0
+    if rank == 0:
+        clips = 4 * bs * world * args.steps
+        line = {'metric': '10s-clips/sec inference %s (pytorch_utils.forward, host int16 in, host numpy out)' % args.model,
+                'value': clips / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'bf16', 'data': 'synthetic',
+                'config': {'workload': 'eval-mode forward loop, 4 batches of %d raw 10 s clips per step' % bs,
+                           'batch_size_per_gpu': bs},
+                'e2e': {'value': clips / (ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(4 * pcm.nbytes),
+                        'd2h_bytes_per_step': int(4 * bs * (1000 * 17 + 17) * 4)},
+                'gpu_launches': launches}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     return 0
 
 
@@ -194,8 +435,9 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=dev)
     from sound_event_detection_dcase2017_task4_b200 import _lib, models
     from sound_event_detection_dcase2017_task4_b200.trainer import FusedTrainer
-    from oracle import sed as _unused  # noqa: F401  (cpu_baseline leg only; never on the timed path)
+    from sound_event_detection_dcase2017_task4_b200.utilities import Mixup
     _lib.lib()
+    MODEL = args.model
 
     bs = args.batch
     b2 = 2 * bs
@@ -207,8 +449,7 @@ def run_ours(args):
     pcm, target_np = synthetic_rank_batch(b2, rank)
     wave_host = torch.from_numpy((pcm / np.float32(32767.)).astype(np.float32)).pin_memory()
     target_host = torch.from_numpy(target_np).pin_memory()
-    from oracle.sed import MixupLambda
-    lam_gen = MixupLambda(1., 1234 + rank)           # utilities.Mixup's numpy stream (host-side, as in main.py:233)
+    lam_gen = Mixup(1., 1234 + rank)                 # utils/utilities.py:220-242 (host-side numpy stream, main.py:233)
     lam_host = torch.empty(b2, dtype=torch.float32).pin_memory()
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
     wave_dev = wave_host.to(dev)
@@ -216,23 +457,30 @@ def run_ours(args):
     lam_dev = torch.empty(b2, dtype=torch.float32, device=dev)
 
     def next_lambda():
-        lam_host.copy_(torch.from_numpy(lam_gen.get_lambda(b2).astype(np.float32)))
+        lam_gen.fill_lambda(lam_host.numpy())
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    per_step = {}
+
+    def timed(fn, steps, tag=None):
+        """EXACTLY `steps` steps between two barrier + synchronize pairs, device time (CUDA events on the compute
+        stream); one extra event per step gives the per-step distribution (median / min) without adding a sync."""
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
         n0 = _lib.launch_count()
-        e0.record()
-        for _ in range(steps):
+        marks[0].record()
+        for i in range(steps):
             fn()
-        e1.record()
+            marks[i + 1].record()
         barrier()
-        ms = e0.elapsed_time(e1)
+        ms = marks[0].elapsed_time(marks[-1])
+        if tag:
+            d = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(steps))
+            per_step[tag] = {'median_ms': round(statistics.median(d), 4), 'min_ms': round(d[0], 4), 'max_ms': round(d[-1], 4)}
         launches = _lib.launch_count() - n0
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -255,7 +503,7 @@ def run_ours(args):
 
     def submit(slot):
         """Step inputs: waveforms + targets + this step's mixup lambdas, pinned host -> device slot."""
-        lam_slots[slot].copy_(torch.from_numpy(lam_gen.get_lambda(b2).astype(np.float32)))
+        lam_gen.fill_lambda(lam_slots[slot].numpy())
         feed.submit(slot, {'waveform': host_wave['cur'], 'target': target_host, 'lam': lam_slots[slot]})
 
     def step_e2e():
@@ -276,12 +524,12 @@ def run_ours(args):
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    ms, launches = timed(step_resident, args.steps)
+    ms, launches = timed(step_resident, args.steps, 'resident')
     clock_info = clocks.stop() if rank == 0 else None
     submit(0)                                            # prologue: first batch (its copy is outside the timed region;
     for _ in range(2):                                   #  each timed step issues exactly one batch copy)
         step_e2e()
-    ms_e2e, _ = timed(step_e2e, args.steps)
+    ms_e2e, _ = timed(step_e2e, args.steps, 'e2e')
     # the same loop fed with int16 PCM (x / 32767 fused into the log-mel kernel's gather: bit-identical log-mel)
     host_wave['cur'] = pcm_host
     stage['slot'] = 0
@@ -361,7 +609,7 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        v, sec = cpu_oracle_run(20, 2, 8, threads)
+        v, sec = cpu_oracle_run(20, 2, 8, threads, MODEL)
         cpu = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                'sample': 'CPU oracle (oracle/sed.py), 2 warm-up + 20 timed steps of batch_size 8 + mixup '
                          '(16 raw 10 s clips/step), %.2f s/step = %.0f s of CPU work' % (sec, 20 * sec)}
@@ -371,19 +619,12 @@ def run_ours(args):
         value = clips / (ms * 1e-3)
         e2e_value = clips / (ms_e2e * 1e-3)
         line = {
-            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'metric': metric_name(MODEL), 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
             'train_samples_per_s': value / 2,
-            'config': {'workload': '%s train step (log-mel, bn0, SpecAugment, mixup, 4 ConvBlocks, biGRU, '
-                                   'attention head, clip_bce, backward, Adam-amsgrad), batch_size %d + mixup '
-                                   '= %d raw 32 kHz x 10 s clips per GPU per step' % (MODEL, bs, b2),
-                       'batch_size_per_gpu': bs, 'raw_clips_per_gpu_per_step': b2,
-                       'parallelism': 'dp%d, one NCCL all-reduce of the flat fp32 gradient per step' % world,
-                       'precision': 'bf16 tensor-core operands / activations, fp32 accumulation, fp32 front-end, '
-                                    'BN statistics, GRU, heads, loss, optimizer',
-                       'l2': 'inputs larger than L2 (waveforms %.0f MB per step, activations > 10 GB)'
-                             % (b2 * CLIP_SAMPLES * 4 / 1e6)},
+            'config': train_config(MODEL, bs, world),
+            'per_step_ms': per_step,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e / args.steps,
                     'h2d_bytes_per_step': int(wave_host.numel() * 4 + target_host.numel() * 4 + b2 * 4),
                     'd2h_bytes_per_step': 4, 'loss': stage.get('loss'),
@@ -415,6 +656,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=256, help='batch_size per GPU (raw clips = 2x under mixup)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--model', default=MODEL, help='any of the seven Cnn_9layers_* classes (default: the metric\'s model)')
+    ap.add_argument('--workload', default='train', choices=['train', 'logmel', 'eval'])
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -424,6 +667,10 @@ def main():
         cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(args.gpus),
                '--master-addr', '127.0.0.1', '--master-port', '29513', os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
+    if args.workload == 'logmel':
+        return run_logmel(args)
+    if args.workload == 'eval':
+        return run_eval(args)
     return run_ours(args)
 
 

@@ -9,7 +9,8 @@ import os
 import threading
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, 'libsedb200.so')
+# SED_B200_LIB: development override (A/B builds made by build.build_variant); the product loads the in-tree library
+LIB_PATH = os.environ.get('SED_B200_LIB') or os.path.join(_PKG_DIR, 'libsedb200.so')
 
 _c_int, _c_ll, _c_float, _c_void_p = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_void_p
 P, I, L, F, D = _c_void_p, _c_int, _c_ll, _c_float, ctypes.c_double

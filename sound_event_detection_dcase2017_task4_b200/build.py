@@ -49,6 +49,20 @@ def _compile(src, force, verbose):
     return obj, r.stderr if verbose else ''
 
 
+def build_variant(tag, defines):
+    """Development: a second library libsedb200_<tag>.so compiled with extra -D switches (A/B runs under gpurun select
+    it with SED_B200_LIB=<path>, see _lib.py).  Not used by the product."""
+    global OBJ_DIR, LIB_PATH, NVCC_FLAGS
+    saved = (OBJ_DIR, LIB_PATH, NVCC_FLAGS)
+    try:
+        OBJ_DIR = os.path.join(PKG_DIR, 'csrc', 'build_' + tag)
+        LIB_PATH = os.path.join(PKG_DIR, 'libsedb200_%s.so' % tag)
+        NVCC_FLAGS = NVCC_FLAGS + ['-D' + d for d in defines]
+        return build(force=False)
+    finally:
+        OBJ_DIR, LIB_PATH, NVCC_FLAGS = saved
+
+
 def build(force=False, verbose=False):
     os.makedirs(OBJ_DIR, exist_ok=True)
     srcs = sources()
@@ -68,4 +82,8 @@ def build(force=False, verbose=False):
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv))
+    if '--variant' in sys.argv:
+        i = sys.argv.index('--variant')
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv))

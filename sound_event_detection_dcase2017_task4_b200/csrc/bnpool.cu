@@ -366,7 +366,20 @@ __device__ __forceinline__ void dyn_retire(int* sched) {
   }
 }
 
-__device__ __forceinline__ uint2 ldg8(const void* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+// 8-byte streaming load.  y / dA are read exactly once per pass: keep them out of L1 (no_allocate) so that the lines do
+// not compete with the shared-memory traffic of a co-resident tensor-core CTA (the carve-out is one SRAM).
+#ifndef SED_BN_LD_MODE
+#define SED_BN_LD_MODE 1
+#endif
+__device__ __forceinline__ uint2 ldg8(const void* p) {
+#if SED_BN_LD_MODE == 1
+  uint2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+#else
+  return __ldg(reinterpret_cast<const uint2*>(p));
+#endif
+}
 __device__ __forceinline__ void unpack4(const uint2& raw, float (&v)[4]) {
   const float2 a = unpack_bf16x2(raw.x), b = unpack_bf16x2(raw.y);
   v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;

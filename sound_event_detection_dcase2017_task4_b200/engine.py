@@ -114,6 +114,11 @@ _SIDE_STREAMS = {}
 # registers with up to 16 KB of shared memory, and the weight-gradient CTA took all 227 KB.  Round 2 rebuilt both sides
 # for co-residency (csrc/bnpool.cu "backward fast paths", csrc/conv_wgrad_tc.cu kWgradSmemBudget).
 OVERLAP_WGRAD = True
+# Layers (index into ctx.layers, 0 = block1.conv1) whose weight gradient may go to the side stream.  The 64 -> 64 layer
+# (index 1) is excluded: its weight-gradient kernel is bound by shared-memory operand reads (SS-mode tcgen05.mma with
+# N = 64), and the BatchNorm-backward loads of layer 0 that it would run beside go through the same L1/shared-memory
+# SRAM -- measured (tools/timeline.py) the reduce pass took 2.4 ms beside it vs 0.7 ms alone, a net loss.
+OVERLAP_LAYERS = frozenset((2, 3, 4, 5, 6, 7))
 # Fold the reduction pass of each BatchNorm backward into the epilogue of the data-gradient kernel that produces its dA
 # (sed_conv3x3_tc_dgrad_bnr).  Correct (tests/test_gpu_conv.py) but measured SLOWER on B200 at batch 256
 # (tools/ab_step.py: 42.1 vs 40.1 ms/step): the 8 epilogue warps cannot hide the HBM latency of the y reads that the
@@ -155,7 +160,7 @@ def trunk_backward(ctx, dfeat, grad_of, overlap_wgrad=None):
                                   grad_of(lc.bn.bias), gy_partial=gy_partial)
         gy_partial = None
         gw = grad_of(lc.conv.weight)
-        side_wgrad = overlap_wgrad and gw is not None and not lc.is_c1
+        side_wgrad = overlap_wgrad and gw is not None and not lc.is_c1 and li in OVERLAP_LAYERS
         if side_wgrad:
             ready = torch.cuda.Event()
             ready.record(main)

@@ -27,26 +27,119 @@ def do_mixup(x, mixup_lambda):
     return x[0::2] * lam[0::2].reshape(shape) + x[1::2] * lam[1::2].reshape(shape)
 
 
-def forward(model, data_loader, return_input=False, return_target=False):
-    """Inference loop of pytorch_utils.py:25-77: eval mode, no grad, per-batch outputs gathered on
-    the host as numpy arrays."""
+class _OutputDrain(object):
+    """Device -> host drain of the per-batch outputs of ``forward``: two sets of pinned host buffers and a copy
+    stream, so the (B, 1000, 17) framewise block of batch n leaves the device while batch n+1 computes (the reference
+    blocks the compute stream twice per batch with ``.data.cpu().numpy()``, pytorch_utils.py:56-61)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.stream = torch.cuda.Stream(device=device)
+        self.slots = [None, None]          # {'key': pinned tensor}
+        self.pending = [None, None]        # (event, {key: (pinned tensor, rows)})
+
+    def submit(self, slot, outputs):
+        """Start copying a dict of device tensors into pinned set ``slot`` (after the kernels that produce them)."""
+        cur = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(cur)
+        bufs = self.slots[slot]
+        if bufs is None or any(k not in bufs or bufs[k].shape[1:] != v.shape[1:] or bufs[k].shape[0] < v.shape[0]
+                               or bufs[k].dtype != v.dtype for k, v in outputs.items()):
+            bufs = self.slots[slot] = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in outputs.items()}
+        taken = {}
+        with torch.cuda.stream(self.stream):
+            for k, v in outputs.items():
+                v = v.detach()
+                bufs[k][:v.shape[0]].copy_(v, non_blocking=True)
+                v.record_stream(self.stream)
+                taken[k] = (bufs[k], v.shape[0])
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.pending[slot] = (ev, taken)
+
+    def collect(self, slot):
+        """Host arrays of the batch last submitted into ``slot`` (waits for its copy only)."""
+        if self.pending[slot] is None:
+            return None
+        ev, taken = self.pending[slot]
+        ev.synchronize()
+        self.pending[slot] = None
+        return {k: buf.numpy()[:rows].copy() for k, (buf, rows) in taken.items()}
+
+
+def pad_framewise_output(framewise_output, frames_num):
+    """(N, T, K) numpy -> (N, frames_num, K): crop, or repeat the last frame.  ``interpolate`` (models.py:58-69)
+    yields 8 * 125 = 1000 frames while the packed ``strong_target`` has 1001 (utils/config.py:14), which trips the
+    shape assertion at pytorch/evaluate.py:19."""
+    n, t, k = framewise_output.shape
+    if frames_num == t:
+        return framewise_output
+    if frames_num < t:
+        return np.ascontiguousarray(framewise_output[:, :frames_num])
+    out = np.empty((n, frames_num, k), dtype=framewise_output.dtype)
+    out[:, :t] = framewise_output
+    out[:, t:] = framewise_output[:, t - 1:t]
+    return out
+
+
+def forward(model, data_loader, return_input=False, return_target=False, frames_num=None):
+    """Inference loop of pytorch_utils.py:25-77: eval mode, no grad, outputs gathered on the host as numpy arrays
+    with the reference's keys and shapes.  int16 PCM waveforms are accepted as they are (x/32767 happens on the
+    device).  ``frames_num``: None keeps the model's own frame count (reference behaviour); an int, or 'target' for
+    the frame count of the batches' ``strong_target``, pads/crops ``framewise_output`` (pad_framewise_output).
+
+    Pipelining: batch n's outputs are drained to pinned host memory on a copy stream while batch n+1 runs; the
+    host only waits for a batch's copy when the NEXT batch has been enqueued."""
     device = next(model.parameters()).device
+    if device.type != 'cuda':
+        raise RuntimeError('forward: the model must live on a CUDA device (no CPU path in this package)')
     output_dict = {}
-    for batch_data_dict in data_loader:
-        batch_waveform = move_data_to_device(batch_data_dict['waveform'], device)
+    drain = _OutputDrain(device)
+
+    def harvest(slot):
+        got = drain.collect(slot)
+        if got is None:
+            return
+        append_to_dict(output_dict, 'clipwise_output', got['clipwise_output'])
+        if 'framewise_output' in got:
+            frame = got['framewise_output']
+            want = pending_frames[slot]
+            if want is not None:
+                frame = pad_framewise_output(frame, want)
+            append_to_dict(output_dict, 'framewise_output', frame)
+
+    pending_frames = [None, None]
+    n = -1
+    for n, batch_data_dict in enumerate(data_loader):
+        slot = n & 1
+        wave = batch_data_dict['waveform']
+        if isinstance(wave, np.ndarray) and wave.dtype == np.int16:
+            batch_waveform = torch.from_numpy(wave).to(device)
+        elif torch.is_tensor(wave):
+            batch_waveform = wave.to(device)
+        else:
+            batch_waveform = move_data_to_device(wave, device)
         with torch.no_grad():
             model.eval()
             batch_output = model(batch_waveform)
-        append_to_dict(output_dict, 'audio_name', batch_data_dict['audio_name'])
-        append_to_dict(output_dict, 'clipwise_output', batch_output['clipwise_output'].data.cpu().numpy())
+        outs = {'clipwise_output': batch_output['clipwise_output']}
         if 'framewise_output' in batch_output.keys():
-            append_to_dict(output_dict, 'framewise_output', batch_output['framewise_output'].data.cpu().numpy())
+            outs['framewise_output'] = batch_output['framewise_output']
+        drain.submit(slot, outs)
+        want = frames_num
+        if want == 'target':
+            want = batch_data_dict['strong_target'].shape[1] if 'strong_target' in batch_data_dict.keys() else None
+        pending_frames[slot] = want
+        harvest(slot ^ 1)                                   # the previous batch: its copy overlapped this launch
+        append_to_dict(output_dict, 'audio_name', batch_data_dict['audio_name'])
         if return_input:
             append_to_dict(output_dict, 'waveform', batch_data_dict['waveform'])
         if return_target:
             for key in ('target', 'strong_target'):
                 if key in batch_data_dict.keys():
                     append_to_dict(output_dict, key, batch_data_dict[key])
+    if n >= 0:
+        harvest(n & 1)
     for key in output_dict.keys():
         output_dict[key] = np.concatenate(output_dict[key], axis=0)
     return output_dict

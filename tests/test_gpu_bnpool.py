@@ -89,7 +89,7 @@ def test_bn_backward_is_bit_reproducible_under_co_scheduling():
     from sound_event_detection_dcase2017_task4_b200 import _lib, ops
     B, H, W, C = 8, 501, 64, 64
     y, bn, g = _setup(B, H, W, C, seed=3)
-    assert _lib.lib().sed_bn_bwd_partials(B, H, W, C, 2, 2) > 148
+    assert _lib.lib().sed_bn_bwd_workspace_rows(B, H, W, C, 2, 2) > 148
     st = ops.bn_finalize(_partial(y), B * H * W, bn)
     dA = torch.randn(B, H // 2, W // 2, C, generator=g).to(torch.bfloat16).cuda()
     outs = []

@@ -289,3 +289,25 @@ def test_trainable_tensors_are_found_on_dataparallel_replicas(name):
     assert all((not t.is_leaf) and t.requires_grad for t in got)
     # the tensors the engine reads through attribute access are those same objects
     assert replica.conv_block3.conv2.weight is got[[id(p) for p in want].index(id(net.conv_block3.conv2.weight))]
+
+
+def test_gradient_exchange_world_size_2_gloo(tmp_path, run_two_ranks):
+    """Row a17 / (e) on CPU: two gloo ranks.  Every rank scales its loss by 1/world, ONE all-reduce(sum) of the flat
+    gradient then holds the gradient of the global-batch mean loss on every rank -- what nn.DataParallel's reduce
+    gives for equal shards (main.py:138).  Shards are contiguous, equal and even-sized (mixup pairs stay together)."""
+    r0, r1 = run_two_ranks('cpu', tmp_path)
+    want = (r0['local'] + r1['local']) / 2
+    assert torch.equal(r0['reduced'], r1['reduced'])
+    assert torch.allclose(r0['reduced'], want, rtol=0, atol=1e-7)
+    assert r0['bounds'] == (0, 32) and r1['bounds'] == (32, 64)
+
+
+def test_shard_bounds_keep_mixup_pairs_together():
+    from sound_event_detection_dcase2017_task4_b200.trainer import shard_bounds
+    for world in (1, 2, 4, 8):
+        edges = [shard_bounds(512 * world, world, r) for r in range(world)]
+        assert edges[0][0] == 0 and edges[-1][1] == 512 * world
+        assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
+        assert all((hi - lo) % 2 == 0 and lo % 2 == 0 for lo, hi in edges)
+    with pytest.raises(ValueError):
+        shard_bounds(6, 4, 0)

@@ -18,7 +18,8 @@ rounds = int(sys.argv[sys.argv.index('--rounds') + 1]) if '--rounds' in sys.argv
 target, values = spec.split('=')
 modname, attr = target.rsplit('.', 1)
 mod = importlib.import_module('sound_event_detection_dcase2017_task4_b200.' + modname)
-values = [int(v) for v in values.split(',')]
+import ast
+values = [ast.literal_eval(v) for v in values.split(';')] if ';' in values or '(' in values else [int(v) for v in values.split(',')]
 
 dev = torch.device('cuda', 0)
 torch.manual_seed(0)
@@ -33,7 +34,7 @@ for _ in range(3):
     trainer.step(wave, tgt, lam)
 for r in range(rounds):
     for v in values:
-        setattr(mod, attr, bool(v))
+        setattr(mod, attr, bool(v) if isinstance(v, int) else frozenset(v))
         trainer.step(wave, tgt, lam)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -42,4 +43,4 @@ for r in range(rounds):
             trainer.step(wave, tgt, lam)
         e1.record()
         torch.cuda.synchronize()
-        print('%s=%d round %d: %.3f ms/step' % (target, v, r, e0.elapsed_time(e1) / steps), flush=True)
+        print('%s=%s round %d: %.3f ms/step' % (target, v, r, e0.elapsed_time(e1) / steps), flush=True)
