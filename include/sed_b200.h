@@ -230,7 +230,10 @@ int sed_gru_bwd(const float* dout, const float* out, const float* gates, const f
  * q/k/v: fp32 (B*T, ld) row-major, head h in columns [h*64, h*64+64): the outputs of the w_qs / w_ks /
  * w_vs projections used in place (replaces the four permute().contiguous() copies).  T <= 128, d = 64.
  * ctx (B*T, H*64); probs (B,H,T,T) = softmax before dropout (saved for the backward, may be NULL).
- * Dropout(p_drop) on the probabilities from Philox4x32-10(seed, offset + element/4); p_drop = 0 in eval.
+ * Every product (Q K^T, P V and the four of the backward) is a warp-level bf16 tensor-core tile product with fp32
+ * accumulators and a hi/lo operand split (fp32-class accuracy); q/k/v/dctx must be 16-byte aligned, ld % 4 == 0.
+ * Dropout(p_drop) on the probabilities from Philox4x32-10(seed, offset + element/4), element = (score row) * 128 +
+ * key (the caller advances its generator by B*H*T*128 draws); p_drop = 0 in eval.
  * bwd: dq/dk/dv use the addressing of q/k/v. */
 int sed_attention_fwd(const float* q, const float* k, const float* v, int ldq, int ldk, int ldv, int B, int T, int H,
                       int d, float temperature, float p_drop, unsigned long long seed, unsigned long long offset,

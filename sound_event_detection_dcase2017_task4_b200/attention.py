@@ -3,8 +3,9 @@
 sites :742, :836 -- always ``multihead(x, x, x)`` with ``mask=None``).
 
     qkv  = x @ [w_qs; w_ks; w_vs]^T + b      one tensor-core GEMM (3-way bf16 split, fp32-class accuracy)
-    ctx  = softmax(q k^T / sqrt(d_k)) [dropout 0.1] v   per (batch, head), fused kernel, heads
-                                              addressed in place (no permute/contiguous copies)
+    ctx  = softmax(q k^T / sqrt(d_k)) [dropout 0.1] v   per (batch, head), one fused tensor-core kernel (warp-level
+                                              bf16x3 MMA tiles, csrc/attention_tc.cu), heads addressed in place (no
+                                              permute/contiguous copies)
     out  = relu(dropout_0.2(ctx @ fc^T + b)) tensor-core GEMM + one elementwise kernel
 
 No residual and no LayerNorm (both are dead code in the reference; ``layer_norm`` stays a
@@ -52,7 +53,7 @@ def multihead_forward(mh, feat, training, keep):
     ld = 3 * h * d
     p_att = float(mh.attention.dropout.p) if training else 0.0
     p_out = float(mh.dropout.p) if training else 0.0
-    seed, off_att = _philox_state(dev, b * h * t * t) if p_att > 0 else (0, 0)
+    seed, off_att = _philox_state(dev, b * h * t * 128) if p_att > 0 else (0, 0)    # element index = score row * 128 + key
     ctx2d = torch.empty((b * t, h * d), dtype=F32, device=dev)
     probs = torch.empty((b, h, t, t), dtype=F32, device=dev) if keep else None
     temperature = float(mh.attention.temperature)

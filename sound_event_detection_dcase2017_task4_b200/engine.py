@@ -153,6 +153,7 @@ def trunk_backward(ctx, dfeat, grad_of, overlap_wgrad=None):
     dev = dA.device
     main, side = _side_stream(dev) if overlap_wgrad else (None, None)
     used_side = False
+    held = []
     gy_partial = None
     for li in range(len(ctx.layers) - 1, -1, -1):
         lc = ctx.layers[li]
@@ -179,8 +180,11 @@ def trunk_backward(ctx, dfeat, grad_of, overlap_wgrad=None):
                 dA = tcconv.conv3x3(dy, lc.wd, cin)                    # bf16 NHWC
             if side_wgrad:
                 side.wait_event(ready)
-                dy.record_stream(side)
-                x_in.record_stream(side)
+                # dy / x_in belong to the main stream's allocator pool.  They are kept alive in `held` until the main
+                # stream has been ordered behind the side stream (end of this function), so whatever reuses their
+                # memory later runs after the weight gradient -- no Tensor.record_stream: its deferred frees made the
+                # caching allocator grow by ~35 GB and cudaMalloc inside timed steps (tools/hiccup.py: one 130 ms step).
+                held.append((dy, x_in))
                 used_side = True
                 with torch.cuda.stream(side):
                     tcconv.conv3x3_wgrad(dy, x_in, out=gw)
@@ -194,6 +198,7 @@ def trunk_backward(ctx, dfeat, grad_of, overlap_wgrad=None):
         done = torch.cuda.Event()
         done.record(side)
         main.wait_event(done)
+    del held
 
 
 # ------------------------------------------------------------------ heads

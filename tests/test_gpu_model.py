@@ -85,7 +85,8 @@ def test_eval_forward_10s_with_trained_like_stats(name):
     assert _rel(o['clipwise_output'].cpu(), c_ref) <= 4e-3
 
 
-@pytest.mark.parametrize('name', ['Cnn_9layers_FrameAvg', 'Cnn_9layers_Gru_FrameAtt'])
+@pytest.mark.parametrize('name', ['Cnn_9layers_FrameAvg', 'Cnn_9layers_Gru_FrameAtt', 'Cnn_9layers_Transformer_FrameAvg',
+                                  'Cnn_9layers_Transformer_FrameAtt'])
 def test_eval_forward_10s_reference_init(name):
     """Full-length 10 s clips at the reference's own initialisation: clip-wise outputs <= 1e-3 rel."""
     from oracle import sed
