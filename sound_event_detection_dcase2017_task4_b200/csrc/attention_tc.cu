@@ -55,17 +55,21 @@ __device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const __nv_bfloat16*
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
 }
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
                "{%0, %1, %2, %3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// c += (ah + al) * (bh + bl) without the lo*lo term
-__device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0,
-                                     uint32_t bh1, uint32_t bl0, uint32_t bl1) {
-  mma16816(c, ah, bh0, bh1);
-  mma16816(c, al, bh0, bh1);
-  mma16816(c, ah, bl0, bl1);
+// (c0, c1) += (ah + al) * (bh + bl) without the lo*lo term, for the two 8-column tiles of one ldmatrix.x4 B load.  The six
+// MMAs alternate between the two accumulators so that back-to-back instructions never depend on each other.
+__device__ __forceinline__ void mma3x2(float (&c0)[4], float (&c1)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                       const uint32_t (&bh)[4], const uint32_t (&bl)[4]) {
+  mma16816(c0, ah, bh[0], bh[1]);
+  mma16816(c1, ah, bh[2], bh[3]);
+  mma16816(c0, al, bh[0], bh[1]);
+  mma16816(c1, al, bh[2], bh[3]);
+  mma16816(c0, ah, bl[0], bl[1]);
+  mma16816(c1, ah, bl[2], bl[3]);
 }
 // fp32 pair -> bf16x2 hi and bf16x2 lo (lo = x - float(hi))
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
@@ -113,8 +117,7 @@ __device__ __forceinline__ void tile_product_nt(float (&acc)[16][4], const __nv_
         uint32_t bh[4], bl[4];
         ldsm_x4(bh, Bh + b_off + np * 16 * kLd + kk * 16);
         ldsm_x4(bl, Bl + b_off + np * 16 * kLd + kk * 16);
-        mma3(acc[2 * np], ah, al, bh[0], bh[1], bl[0], bl[1]);
-        mma3(acc[2 * np + 1], ah, al, bh[2], bh[3], bl[2], bl[3]);
+        mma3x2(acc[2 * np], acc[2 * np + 1], ah, al, bh, bl);
       }
     }
   }
@@ -130,8 +133,7 @@ __device__ __forceinline__ void tile_accumulate_nn(float (&out)[8][4], const uin
     uint32_t bh[4], bl[4];
     ldsm_x4_t(bh, Bh + b_off + nd * 16);
     ldsm_x4_t(bl, Bl + b_off + nd * 16);
-    mma3(out[2 * nd], ah, al, bh[0], bh[1], bl[0], bl[1]);
-    mma3(out[2 * nd + 1], ah, al, bh[2], bh[3], bl[2], bl[3]);
+    mma3x2(out[2 * nd], out[2 * nd + 1], ah, al, bh, bl);
   }
 }
 
