@@ -111,7 +111,7 @@ constexpr int kC1Ld = 72;                 // bf16 elements per staged input row 
 constexpr int kC1Plane = (kRows + 2) * kC1Ld;
 
 __device__ __forceinline__ void mma16816_c1(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
                "{%0, %1, %2, %3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(kThreadsC1, 2)
 conv_c1_fwd_mma_kernel(const float* __restrict__ x, const float* __restrict__ w /* (64, 9) */, int B, int H, int W,
                        __nv_bfloat16* __restrict__ y, float* __restrict__ partial) {
   constexpr int Cout = 64;
-  __shared__ __align__(16) __nv_bfloat16 s_in[2 * kC1Plane];              // hi plane, lo plane
+  __shared__ __align__(16) __nv_bfloat16 s_in[2 * 2 * kC1Plane];          // two buffers of (hi plane, lo plane)
   __shared__ __align__(16) __nv_bfloat16 s_out[(kThreadsC1 / 32) * 16 * kC1Ld];
   __shared__ float s_red[(kThreadsC1 / 32) * 2 * Cout];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
@@ -178,28 +178,52 @@ conv_c1_fwd_mma_kernel(const float* __restrict__ x, const float* __restrict__ w 
   float2 sum[8], sq[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) sum[j] = sq[j] = make_float2(0.f, 0.f);
-  const unsigned short* s_in16 = reinterpret_cast<const unsigned short*>(s_in);
   __nv_bfloat16* st = s_out + warp * 16 * kC1Ld;
   const int tiles_w = W >> 4;
   const int chunks = (H + kRows - 1) / kRows;
   const int items = B * chunks;
+  const int ldx = W + 2;
+  // The input rows of item n+1 are fetched into registers while item n computes and written (split into bf16 hi / lo
+  // planes, zero borders) into the other shared-memory buffer afterwards: the global-load latency of the tiny input
+  // never sits between two barriers.  (kRows + 2) * (W + 2) <= 3 * 256 elements = 3 per thread.
+  float pf[3];
+  auto fetch = [&](int it) {
+    const int b = it / chunks, h0 = (it - b * chunks) * kRows;
+    const int nr = min(kRows, H - h0);
+    const float* img = x + (long long)b * H * W;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int i = threadIdx.x + q * kThreadsC1;
+      const int r = i / ldx, c = i - r * ldx;
+      const int h = h0 - 1 + r, wc = c - 1;
+      pf[q] = (r < nr + 2 && h >= 0 && h < H && wc >= 0 && wc < W) ? __ldg(img + (long long)h * W + wc) : 0.f;
+    }
+  };
+  auto stash = [&](int buf) {
+    __nv_bfloat16* dst = s_in + buf * 2 * kC1Plane;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int i = threadIdx.x + q * kThreadsC1;
+      const int r = i / ldx, c = i - r * ldx;
+      if (r < kRows + 2) {
+        const __nv_bfloat16 hi = __float2bfloat16_rn(pf[q]);
+        dst[r * kC1Ld + c] = hi;
+        dst[kC1Plane + r * kC1Ld + c] = __float2bfloat16_rn(pf[q] - __bfloat162float(hi));
+      }
+    }
+  };
+  int cur = 0;
+  if ((int)blockIdx.x < items) {
+    fetch(blockIdx.x);
+    stash(0);
+  }
+  __syncthreads();
   for (int item = blockIdx.x; item < items; item += gridDim.x) {
     const int b = item / chunks, h0 = (item - b * chunks) * kRows;
     const int nr = min(kRows, H - h0);
-    __syncthreads();
-    {   // stage rows h0-1 .. h0+nr as bf16 hi / lo planes, zero borders
-      const float* img = x + (long long)b * H * W;
-      const int ldx = W + 2;
-      for (int i = threadIdx.x; i < (nr + 2) * ldx; i += kThreadsC1) {
-        const int r = i / ldx, c = i - r * ldx;
-        const int h = h0 - 1 + r, wc = c - 1;
-        const float v = (h >= 0 && h < H && wc >= 0 && wc < W) ? __ldg(img + (long long)h * W + wc) : 0.f;
-        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-        s_in[r * kC1Ld + c] = hi;
-        s_in[kC1Plane + r * kC1Ld + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
-      }
-    }
-    __syncthreads();
+    const int next = item + gridDim.x;
+    if (next < items) fetch(next);
+    const unsigned short* s_in16 = reinterpret_cast<const unsigned short*>(s_in + cur * 2 * kC1Plane);
     for (int tile = warp; tile < nr * tiles_w; tile += kThreadsC1 / 32) {
       const int r = tile / tiles_w, w0 = (tile - r * tiles_w) << 4;
       const int base0 = r * kC1Ld + w0 + g, base1 = base0 + 8;       // window top-left of pixels w0+g and w0+g+8
@@ -238,6 +262,9 @@ conv_c1_fwd_mma_kernel(const float* __restrict__ x, const float* __restrict__ w 
         *reinterpret_cast<uint4*>(dst + px * Cout + ch) = *reinterpret_cast<const uint4*>(st + px * kC1Ld + ch);
       }
     }
+    if (next < items) stash(cur ^ 1);
+    __syncthreads();
+    cur ^= 1;
   }
   if (partial == nullptr) return;
   // ---- per-CTA statistics row: lanes with the same t4 hold the same channels -> fold the 8 row groups, then the warps
@@ -282,7 +309,7 @@ int sed_conv_c1_fwd(const float* x, const float* w, void* y, float* stats_partia
   SED_REQUIRE(Cout % 8 == 0 && Cout <= 256 && 256 % (Cout / 8) == 0, "sed_conv_c1_fwd: Cout=%d unsupported", Cout);
   if (B == 0) return 0;
   SED_REQUIRE(W >= 1 && W <= 1024, "sed_conv_c1_fwd: W=%d out of range", W);
-  if (Cout == 64 && W % 16 == 0 && W + 2 <= kC1Ld && aligned(y, 16)) {
+  if (Cout == 64 && W % 16 == 0 && W + 2 <= kC1Ld && (kRows + 2) * (W + 2) <= 3 * kThreadsC1 && aligned(y, 16)) {
     conv_c1_fwd_mma_kernel<<<sed_conv_c1_grid(), kThreadsC1, 0, (cudaStream_t)stream>>>(
         x, w, B, H, W, reinterpret_cast<__nv_bfloat16*>(y), stats_partial);
     SED_LAUNCH_CHECK("conv_c1_fwd_mma_kernel");

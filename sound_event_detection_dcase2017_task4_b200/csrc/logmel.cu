@@ -3,16 +3,9 @@
 // Replaces torchlibrosa.stft.Spectrogram + LogmelFilterBank as called at
 // /root/reference/pytorch/models.py:199-200 (ctor contracts :166-173).  The reference evaluates
 // the windowed DFT as two dense fp32 conv1d (2.1 GFLOP per 10 s clip) and materialises the
-// (T,513) power spectrogram; here every frame is a shared-memory radix-8 real FFT and only the
+// (T,513) power spectrogram; here every frame is a real 1024-point FFT done by ONE WARP in registers
+// (512-point complex FFT of z[n] = x[2n] + i x[2n+1] + the even/odd split, see logmel_warp_kernel) and only the
 // (T,64) log-mel leaves the SM.
-//
-// Work decomposition: a CTA (256 threads) owns FPC consecutive frames of one clip.  The frames
-// overlap 1024/hop = 3.2x, so the CTA loads the contiguous sample span once (coalesced float4 /
-// int4, reflect padding folded into the gather) and runs 4 frames at a time, 64 threads each:
-//   real 1024-FFT  =  512-point complex FFT of z[n] = x[2n] + i x[2n+1]  (8 x 8 x 8, three
-//   radix-8 passes, one complex value per (thread, r)), then the even/odd split.
-// Persistent grid: CTAs stride over (clip, chunk) work items so the twiddle / window prologue
-// is paid once per CTA.
 #include "common.cuh"
 
 namespace sed {
@@ -21,15 +14,12 @@ namespace {
 constexpr int kNfft = 1024;
 constexpr int kBins = kNfft / 2 + 1;   // 513
 constexpr int kHalf = kNfft / 2;       // 512 complex points
-constexpr int kThreads = 256;
-constexpr int kSlots = 4;              // frames in flight per CTA
-constexpr int kFramesPerChunk = 16;
-constexpr int kBuf = 8 * 72;           // one padded SoA plane of the 512-point work buffer
+constexpr int kFramesPerChunk = 16;    // consecutive frames of a clip per work item (upper bound)
 // Mel projection schedule (built once per CTA in shared memory): every mel filter is cut into pieces of at most
-// kPieceTaps consecutive taps; piece p is owned by thread p % 64 of a frame slot.  The reference bank has 866 taps in
+// kPieceTaps consecutive taps; piece p is owned by lane p % 32 of the frame's warp.  The reference bank has 866 taps in
 // filters of 3..47 taps: one thread per filter made the 47-tap thread the critical path and every weight a scattered
-// 4-byte global load (ncu r01: 78 % excessive sectors, L1/TEX 80 % busy).  Pieces balance the slot (<= 22 taps per
-// thread instead of 47) and the weights are staged tap-major / piece-minor so a warp reads them without conflicts.
+// 4-byte global load (ncu r01: 78 % excessive sectors, L1/TEX 80 % busy).  Pieces balance the lanes (<= 34 taps per
+// lane, 27 on average) and the weights are staged tap-major / piece-minor so a warp reads them without conflicts.
 constexpr int kPieceTaps = 16;
 constexpr int kMaxPieces = 128;
 constexpr int kMaxMels = 128;
@@ -81,14 +71,6 @@ __device__ __forceinline__ void dft8(float2 (&v)[8]) {
   dft4(b0, b1, b2, b3, v[1], v[3], v[5], v[7]);
 }
 
-// the 64 threads (2 warps) of one frame slot only exchange data among themselves: a named barrier per slot lets the
-// four slots of a CTA drift apart instead of meeting at a CTA-wide barrier five times per frame
-__device__ __forceinline__ void slot_barrier(int slot) {
-  asm volatile("bar.sync %0, 64;" ::"r"(slot + 1) : "memory");
-}
-
-__device__ __forceinline__ int zaddr(int k) { return k + 4 * (k >> 5); }   // padded Z layout (<576)
-
 template <typename T> struct Sample;
 template <> struct Sample<float> {
   static __device__ __forceinline__ float cvt(float v) { return v; }
@@ -108,49 +90,85 @@ struct MelBank {
   float amin, db_offset;
 };
 
+// 16-point forward DFT in registers, natural order in and out: two DFT8 (even / odd inputs) + one radix-2 stage
+__device__ __forceinline__ void dft16(float2 (&v)[16]) {
+  const float h = 0.70710678118654752440f, c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;
+  float2 a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { a[i] = v[2 * i]; b[i] = v[2 * i + 1]; }
+  dft8(a);
+  dft8(b);
+  // b[q] *= W16^q,  W16 = exp(-i pi / 8)
+  b[1] = cmul(b[1], make_float2(c1, -s1));
+  b[2] = make_float2(h * (b[2].x + b[2].y), h * (b[2].y - b[2].x));
+  b[3] = cmul(b[3], make_float2(s1, -c1));
+  b[4] = mul_neg_i(b[4]);
+  b[5] = cmul(b[5], make_float2(-s1, -c1));
+  b[6] = make_float2(h * (b[6].y - b[6].x), -h * (b[6].x + b[6].y));
+  b[7] = cmul(b[7], make_float2(-c1, -s1));
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    v[q] = cadd(a[q], b[q]);
+    v[q + 8] = csub(a[q], b[q]);
+  }
+}
+__device__ __forceinline__ float2 shfl2(float2 v, int src) {
+  return make_float2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+__device__ __forceinline__ float2 shfl2_xor(float2 v, int m) {
+  return make_float2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
+}
+__device__ __forceinline__ float2 sel2(bool c, float2 a, float2 b) { return make_float2(c ? a.x : b.x, c ? a.y : b.y); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// One frame per WARP (round 2).  The round-1 kernel gave a frame to 64 threads and exchanged data through shared
+// memory five times per frame (three radix-8 passes, the real-FFT split, the power spectrum): 459 shared-memory
+// wavefronts and ~1680 warp instructions per frame, 28 % of them address arithmetic, with five named barriers
+// (ncu, profiles/r02_logmel_ncu.md).  Here lane L of a warp holds 16 complex values and the 512-point complex FFT is
+//   z[n], n = L + 32 m            lane L, slot m        (coalesced 8-byte loads, window in registers)
+//   DFT16 over m                  -> E_h[q]             in registers              (r = L & 15, h = L >> 4)
+//   radix-2 across lanes L, L^16  -> Zr[kj]             one shuffle exchange: the 32-point DFT over n = r + 16 j'
+//   transpose T[r][kj]            -> lane kj, slot r    the ONLY shared-memory exchange of the transform
+//   twiddle W512^(r kj), DFT16 over r -> Z[kj + 32 kr'] in registers
+// and the real-FFT split pairs bin k = kj + 32 kr' with 512 - k, which lives in lane 32 - kj, slot 15 - kr': a fixed
+// lane permutation, i.e. one more shuffle exchange (lane 0 pairs with itself: its slots are rotated by one first).
+// Nothing but __syncwarp() orders the frame; a CTA is four independent warps walking consecutive frames so that the
+// 3.2x overlap of neighbouring frames is served by L1.
+constexpr int kWarpsW = 4;
+constexpr int kThreadsW = kWarpsW * 32;
+constexpr int kTS = 33;                      // float2 stride of the transpose rows (odd: conflict-free both ways)
+constexpr int kPLen = 520;                   // 513 power bins + padding
+
+template <typename InT>
+__device__ __forceinline__ float2 load_pair(const InT* __restrict__ src, long long i);
+template <>
+__device__ __forceinline__ float2 load_pair<float>(const float* __restrict__ src, long long i) {
+  return __ldg(reinterpret_cast<const float2*>(src + i));
+}
+template <>
+__device__ __forceinline__ float2 load_pair<int16_t>(const int16_t* __restrict__ src, long long i) {
+  const int raw = __ldg(reinterpret_cast<const int*>(src + i));
+  return make_float2(Sample<int16_t>::cvt((int16_t)(raw & 0xFFFF)), Sample<int16_t>::cvt((int16_t)(raw >> 16)));
+}
+
 // kPower: write the 513-bin power spectrogram instead of the log-mel (unfused seam A).
 template <typename InT, bool kPower>
-__global__ void __launch_bounds__(kThreads, 3)
-logmel_kernel(const InT* __restrict__ wave, int n_clips, int n_samples, int hop, int n_frames,
-              int chunks_per_clip, MelBank mel, float* __restrict__ out) {
+__global__ void __launch_bounds__(kThreadsW, 3)
+logmel_warp_kernel(const InT* __restrict__ wave, int n_clips, int n_samples, int hop, int n_frames, int frames_per_item,
+                   int items_per_clip, int pair_ok, MelBank mel, float* __restrict__ out) {
   extern __shared__ __align__(16) float smem[];
-  float* s_work = smem;                      // [kSlots][4][kBuf]  A.re A.im B.re B.im
-  float* s_wil = s_work + kSlots * 4 * kBuf;   // [kPieceTaps][kMaxPieces] mel weights, tap-major (kPower: unused)
-  float* s_part = s_wil + kPieceTaps * kMaxPieces;                 // [kSlots][kMaxPieces] per-piece partial sums
-  int* s_pk0 = reinterpret_cast<int*>(s_part + kSlots * kMaxPieces);   // [kMaxPieces] first FFT bin of the piece
-  int* s_pn = s_pk0 + kMaxPieces;              // [kMaxPieces] taps in the piece
-  int* s_first = s_pn + kMaxPieces;            // [kMaxMels + 1] first piece of every mel filter
-  float* s_span = reinterpret_cast<float*>(s_first + kMaxMels + 4);    // [(FPC-1)*hop + 1024], 16-byte aligned
+  float* s_wil = smem;                                             // [kPieceTaps][kMaxPieces] mel weights, tap-major
+  int* s_pk0 = reinterpret_cast<int*>(s_wil + kPieceTaps * kMaxPieces);      // [kMaxPieces] first FFT bin of a piece
+  int* s_pn = s_pk0 + kMaxPieces;                                  // [kMaxPieces] taps in the piece
+  int* s_first = s_pn + kMaxPieces;                                // [kMaxMels + 4] first piece of every filter
+  float* s_warp = reinterpret_cast<float*>(s_first + kMaxMels + 4);          // per warp: T, P, part
   __shared__ int s_npieces;
+  const int tid = threadIdx.x, warp = tid >> 5, L = tid & 31;
+  float2* T = reinterpret_cast<float2*>(s_warp + warp * (2 * 16 * kTS + kPLen + kMaxPieces));
+  float* P = reinterpret_cast<float*>(T + 16 * kTS);
+  float* part = P + kPLen;
 
-  const int tid = threadIdx.x;
-  const int slot = tid >> 6;
-  const int j = tid & 63;
-  float* A_re = s_work + slot * 4 * kBuf;
-  float* A_im = A_re + kBuf;
-  float* B_re = A_im + kBuf;
-  float* B_im = B_re + kBuf;
-
-  // ---- prologue: everything a thread needs for every frame lives in its registers -----------
-  // (the window samples and split twiddles used to be re-read from shared memory for every frame: the kernel is
-  //  shared-memory-bandwidth bound, so they are per-thread constants now)
-  float2 tw1[8], tw2[8];                      // W512^(j q)  and  W64^(j0 p)
-  float2 win[8];                              // periodic Hann at samples 2(j + 64 r), 2(j + 64 r) + 1
-  float2 tws[4];                              // W1024^(j + 64 s), s = 0..3, for the even/odd split
-  {
-    const int j0 = j & 7;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      tw1[q] = twiddle((j * q) & 511, 512);
-      tw2[q] = twiddle((j0 * q) & 63, 64);
-      const int n2 = 2 * (j + 64 * q);
-      win[q] = make_float2(0.5f - 0.5f * cospif(2.0f * (float)n2 / (float)kNfft),
-                           0.5f - 0.5f * cospif(2.0f * (float)(n2 + 1) / (float)kNfft));
-    }
-#pragma unroll
-    for (int sI = 0; sI < 4; ++sI) tws[sI] = twiddle(j + 64 * sI, kNfft);
-  }
-
+  // ---- mel projection schedule (see kPieceTaps), once per CTA
   if (!kPower) {
     if (tid == 0) {
       int np = 0;
@@ -166,10 +184,9 @@ logmel_kernel(const InT* __restrict__ wave, int n_clips, int n_samples, int hop,
       s_first[mel.n_mels] = np;
       s_npieces = np;
     }
-    for (int i = tid; i < kPieceTaps * kMaxPieces; i += kThreads) s_wil[i] = 0.f;
+    for (int i = tid; i < kPieceTaps * kMaxPieces; i += kThreadsW) s_wil[i] = 0.f;
     __syncthreads();
-    // weights: tap t of filter m belongs to piece s_first[m] + (t - off[m]) / kPieceTaps, position (t - off[m]) % kPieceTaps
-    for (int m = tid; m < mel.n_mels; m += kThreads) {
+    for (int m = tid; m < mel.n_mels; m += kThreadsW) {
       const int o0 = mel.off[m], n = mel.off[m + 1] - o0, p0 = s_first[m];
       for (int i = 0; i < n; ++i) s_wil[(i % kPieceTaps) * kMaxPieces + p0 + i / kPieceTaps] = mel.w[o0 + i];
     }
@@ -177,151 +194,122 @@ logmel_kernel(const InT* __restrict__ wave, int n_clips, int n_samples, int hop,
   }
   const int n_pieces = kPower ? 0 : s_npieces;
 
-  const long long total_items = (long long)n_clips * chunks_per_clip;
-  for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
-    const int clip = (int)(item / chunks_per_clip);
-    const int chunk = (int)(item % chunks_per_clip);
-    const int frame0 = chunk * kFramesPerChunk;
-    const int frames_here = min(kFramesPerChunk, n_frames - frame0);
-    const InT* __restrict__ src = wave + (long long)clip * n_samples;
-    // ---- load the sample span [frame0*hop - 512, ...) with reflect padding ------------------
-    const long long i0 = (long long)frame0 * hop - kHalf;          // original index of span[0]
-    const int need = (frames_here - 1) * hop + kNfft;
-    __syncthreads();                                               // previous item done with s_span
-    const bool interior = (i0 >= 0) && (i0 + need <= n_samples);
-    if (interior && sizeof(InT) == 4 && ((reinterpret_cast<uintptr_t>(src + i0) & 15) == 0)) {
-      const float4* s4 = reinterpret_cast<const float4*>(src + i0);
-      float4* d4 = reinterpret_cast<float4*>(s_span);
-      for (int v = tid; v < (need >> 2); v += kThreads) d4[v] = __ldg(s4 + v);
-      for (int s = (need & ~3) + tid; s < need; s += kThreads) s_span[s] = Sample<InT>::cvt(src[i0 + s]);
-    } else if (interior && sizeof(InT) == 2 && ((reinterpret_cast<uintptr_t>(src + i0) & 15) == 0)) {
-      const int4* s8 = reinterpret_cast<const int4*>(src + i0);
-      for (int v = tid; v < (need >> 3); v += kThreads) {
-        int4 raw = __ldg(s8 + v);
-        const int16_t* p = reinterpret_cast<const int16_t*>(&raw);
+  // ---- per-lane constants
+  const int r_ = L & 15, h_ = L >> 4;
+  float2 win[16];           // 0.5 * periodic Hann at samples 2 (L + 32 m), 2 (L + 32 m) + 1 (the 0.5 is the 1/2 of the real-FFT split)
+  float2 w3[8];             // W32^(i + 8 h)
+  float2 w5[15];            // W512^(r L), r = 1..15
+  float2 w7[8];             // -i W1024^(L + 32 kp)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) s_span[v * 8 + e] = Sample<int16_t>::cvt(p[e]);
-      }
-      for (int s = (need & ~7) + tid; s < need; s += kThreads) s_span[s] = Sample<InT>::cvt(src[i0 + s]);
-    } else {
-      for (int s = tid; s < need; s += kThreads) {
-        long long i = i0 + s;
-        if (i < 0) i = -i;
-        if (i >= n_samples) i = 2LL * (n_samples - 1) - i;
-        float v = 0.f;
-        if (i >= 0 && i < n_samples) v = Sample<InT>::cvt(src[i]);
-        s_span[s] = v;
-      }
-    }
-    __syncthreads();
+  for (int m = 0; m < 16; ++m) {
+    const int n2 = 2 * (L + 32 * m);
+    win[m] = make_float2(0.25f - 0.25f * cospif(2.0f * (float)n2 / (float)kNfft),
+                         0.25f - 0.25f * cospif(2.0f * (float)(n2 + 1) / (float)kNfft));
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    w3[i] = twiddle(i + 8 * h_, 32);
+    const float2 wk = twiddle(L + 32 * i, kNfft);
+    w7[i] = make_float2(wk.y, -wk.x);                              // -i (x + i y) = y - i x
+  }
+#pragma unroll
+  for (int r = 1; r < 16; ++r) w5[r - 1] = twiddle((r * L) & 511, 512);
 
-    for (int fbase = 0; fbase < frames_here; fbase += kSlots) {
-      const int f = fbase + slot;                 // frame within the chunk
-      const bool live = f < frames_here;
-      float2 v[8];
-      // ---- pass 1: DFT8 over r of z[j + 64 r], twiddle W512^(j q) -> A[q][j] -----------------
-      if (live) {
-        const float* x = s_span + f * hop;
+  const long long total_items = (long long)n_clips * items_per_clip;
+  for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
+    const int clip = (int)(item / items_per_clip);
+    const int frame0 = (int)(item % items_per_clip) * frames_per_item;
+    const int frames_here = min(frames_per_item, n_frames - frame0);
+    const InT* __restrict__ src = wave + (long long)clip * n_samples;
+    for (int f = warp; f < frames_here; f += kWarpsW) {
+      const int frame = frame0 + f;
+      const long long i0 = (long long)frame * hop - kHalf;         // sample index of the frame's first tap
+      float2 v[16];
+      // ---- load + window
+      if (pair_ok && i0 >= 0 && i0 + kNfft <= n_samples) {
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const int n2 = 2 * (j + 64 * r);             // 8-byte aligned: hop and n2 are even
-          const float2 xs = *reinterpret_cast<const float2*>(x + n2);
-          v[r] = make_float2(xs.x * win[r].x, xs.y * win[r].y);
+        for (int m = 0; m < 16; ++m) {
+          const float2 xs = load_pair<InT>(src, i0 + 2 * (L + 32 * m));
+          v[m] = make_float2(xs.x * win[m].x, xs.y * win[m].y);
         }
-        dft8(v);
+      } else {                                                      // clip edges: reflect padding, element by element
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float2 y = (q == 0) ? v[0] : cmul(v[q], tw1[q]);
-          A_re[q * 72 + j] = y.x;
-          A_im[q * 72 + j] = y.y;
-        }
-      }
-      slot_barrier(slot);
-      // ---- pass 2: thread (q, j0): DFT8 over j1 of A[q][j0 + 8 j1], twiddle W64^(j0 p) -> B --
-      if (live) {
-        const int q = j >> 3, j0 = j & 7;
+        for (int m = 0; m < 16; ++m) {
+          float xs[2];
 #pragma unroll
-        for (int j1 = 0; j1 < 8; ++j1) v[j1] = make_float2(A_re[q * 72 + j0 + 8 * j1], A_im[q * 72 + j0 + 8 * j1]);
-        dft8(v);
-#pragma unroll
-        for (int p = 0; p < 8; ++p) {
-          float2 u = (p == 0) ? v[0] : cmul(v[p], tw2[p]);
-          B_re[q * 72 + j0 * 9 + p] = u.x;
-          B_im[q * 72 + j0 * 9 + p] = u.y;
+          for (int e = 0; e < 2; ++e) {
+            long long i = i0 + 2 * (L + 32 * m) + e;
+            if (i < 0) i = -i;
+            if (i >= n_samples) i = 2LL * (n_samples - 1) - i;
+            xs[e] = (i >= 0 && i < n_samples) ? Sample<InT>::cvt(src[i]) : 0.f;
+          }
+          v[m] = make_float2(xs[0] * win[m].x, xs[1] * win[m].y);
         }
       }
-      slot_barrier(slot);
-      // ---- pass 3: thread (q, p): DFT8 over j0 -> Z[q + 8 p + 64 s] -> A (padded linear) -----
-      if (live) {
-        const int q = j >> 3, p = j & 7;
+      // ---- DFT16 over m:  E_h[q]
+      dft16(v);
+      // ---- 32-point DFT over j' = h + 2 m for row r: lanes L and L ^ 16 exchange half of their E
+      float2 zl[8], zh[8];
 #pragma unroll
-        for (int j0 = 0; j0 < 8; ++j0) v[j0] = make_float2(B_re[q * 72 + j0 * 9 + p], B_im[q * 72 + j0 * 9 + p]);
-        dft8(v);
+      for (int i = 0; i < 8; ++i) {
+        const float2 snd = sel2(h_ != 0, v[i], v[i + 8]);
+        const float2 rcv = shfl2_xor(snd, 16);
+        const float2 a = sel2(h_ != 0, rcv, v[i]);
+        const float2 b = sel2(h_ != 0, v[i + 8], rcv);
+        const float2 t = cmul(b, w3[i]);
+        zl[i] = cadd(a, t);                                         // kj = i + 8 h
+        zh[i] = csub(a, t);                                         // kj = i + 8 h + 16
+      }
+      // ---- transpose: lane (r, h) -> T[r][kj];  lane kj <- T[r][kj], r = 0..15
 #pragma unroll
-        for (int s = 0; s < 8; ++s) {
-          const int k = q + 8 * p + 64 * s;
-          A_re[zaddr(k)] = v[s].x;
-          A_im[zaddr(k)] = v[s].y;
-        }
+      for (int i = 0; i < 8; ++i) {
+        T[r_ * kTS + i + 8 * h_] = zl[i];
+        T[r_ * kTS + i + 8 * h_ + 16] = zh[i];
       }
-      slot_barrier(slot);
-      // ---- even/odd split -> power spectrum P[0..512] -> B_re ---------------------------------
-      float* P = B_re;                              // 513 <= kBuf
-      // Bins k and 512-k share their inputs: with E = (Z[k] + conj Z[512-k])/2, O = (Z[k] - conj Z[512-k])/(2i) and
-      // t = W1024^k O,  X[k] = E + t  and  X[512-k] = conj(E - t).  Thread j takes k = j + 64 s, s = 0..3 (and their
-      // partners 512-k; k = 0 pairs with the Nyquist bin), thread 0 also the self-paired k = 256.
-      if (live) {
+      __syncwarp();
 #pragma unroll
-        for (int sI = 0; sI < 4; ++sI) {
-          const int k = j + 64 * sI;
-          const int km = (kHalf - k) & (kHalf - 1);
-          const float2 zk = make_float2(A_re[zaddr(k)], A_im[zaddr(k)]);
-          const float2 zm = make_float2(A_re[zaddr(km)], -A_im[zaddr(km)]);   // conj Z[512-k]
-          const float2 e = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y + zm.y));
-          const float2 d = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y - zm.y));
-          const float2 t = cmul(tws[sI], mul_neg_i(d));                       // W^k (Zk - conj Zm) / (2i)
-          const float2 xp = cadd(e, t), xm = csub(e, t);
-          P[k] = xp.x * xp.x + xp.y * xp.y;
-          P[kHalf - k] = xm.x * xm.x + xm.y * xm.y;
-        }
-        if (j == 0) {                               // k = 256: Z[256] pairs with itself, W1024^256 = -i
-          const float2 z = make_float2(A_re[zaddr(256)], A_im[zaddr(256)]);
-          P[256] = z.x * z.x + z.y * z.y;           // |Re z - i Im z|^2
-        }
+      for (int r = 0; r < 16; ++r) v[r] = T[r * kTS + L];
+      __syncwarp();
+#pragma unroll
+      for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], w5[r - 1]);
+      // ---- DFT16 over r:  v[kr'] = Z[L + 32 kr']  (half scale)
+      dft16(v);
+      // ---- real-FFT split + power:  bins k = L + 32 kp (kp < 8) and 512 - k
+      const int src_lane = (32 - L) & 31;
+#pragma unroll
+      for (int kp = 0; kp < 8; ++kp) {
+        const float2 snd = sel2(L == 0, v[(16 - kp) & 15], v[15 - kp]);
+        float2 zm = shfl2(snd, src_lane);                           // Z[512 - k]
+        zm.y = -zm.y;
+        const float2 e = cadd(v[kp], zm), d = csub(v[kp], zm);
+        const float2 t = cmul(d, w7[kp]);
+        const float2 xp = cadd(e, t), xm = csub(e, t);
+        P[L + 32 * kp] = xp.x * xp.x + xp.y * xp.y;
+        P[kHalf - (L + 32 * kp)] = xm.x * xm.x + xm.y * xm.y;
       }
-      slot_barrier(slot);
-      if (live) {
-        const long long frame = (long long)clip * n_frames + frame0 + f;
-        if (kPower) {
-          float* dst = out + frame * kBins;
-          for (int k = j; k < kBins; k += 64) dst[k] = P[k];
-        }
-      }
-      if (!kPower) {
-        // mel projection in two balanced steps: per-piece partial sums, then one thread per filter adds its pieces
-        // in fixed order, converts to dB and stores (64 consecutive floats per frame).
-        float* part = s_part + slot * kMaxPieces;
-        if (live) {
-          for (int p = j; p < n_pieces; p += 64) {
-            const int k0 = s_pk0[p], n = s_pn[p];
-            float acc = 0.f;
+      if (L == 0) P[256] = 4.0f * (v[8].x * v[8].x + v[8].y * v[8].y);   // self-paired bin: |X[256]|^2 = |Z[256]|^2
+      __syncwarp();
+      const long long gframe = (long long)clip * n_frames + frame;
+      if (kPower) {
+        float* dst = out + gframe * kBins;
+        for (int k = L; k < kBins; k += 32) dst[k] = P[k];
+      } else {
+        for (int p = L; p < n_pieces; p += 32) {
+          const int k0 = s_pk0[p], n = s_pn[p];
+          float acc = 0.f;
 #pragma unroll 4
-            for (int i = 0; i < n; ++i) acc = fmaf(s_wil[i * kMaxPieces + p], P[k0 + i], acc);
-            part[p] = acc;
-          }
+          for (int i = 0; i < n; ++i) acc = fmaf(s_wil[i * kMaxPieces + p], P[k0 + i], acc);
+          part[p] = acc;
         }
-        slot_barrier(slot);
-        if (live) {
-          const long long frame = (long long)clip * n_frames + frame0 + f;
-          float* dst = out + frame * mel.n_mels;
-          for (int m = j; m < mel.n_mels; m += 64) {
-            float acc = 0.f;
-            for (int p = s_first[m]; p < s_first[m + 1]; ++p) acc += part[p];
-            dst[m] = 10.0f * log10f(fmaxf(acc, mel.amin)) - mel.db_offset;
-          }
+        __syncwarp();
+        float* dst = out + gframe * mel.n_mels;
+        for (int m = L; m < mel.n_mels; m += 32) {
+          float acc = 0.f;
+          for (int p = s_first[m]; p < s_first[m + 1]; ++p) acc += part[p];
+          dst[m] = 10.0f * log10f(fmaxf(acc, mel.amin)) - mel.db_offset;
         }
       }
-      // next iteration's pass 1 only writes A; B (=P) is rewritten after the next barrier.
+      __syncwarp();
     }
   }
 }
@@ -335,24 +323,23 @@ int launch_logmel(const InT* wave, int n_clips, int n_samples, int hop, MelBank 
   SED_REQUIRE(aligned(out, 4) && aligned(wave, sizeof(InT)), "%s: misaligned pointer", name);
   if (n_clips == 0) return 0;
   SED_REQUIRE(wave && out, "%s: null pointer", name);
-  const int n_frames = n_samples / hop + 1;
-  const int chunks = ceil_div(n_frames, kFramesPerChunk);
   SED_REQUIRE(kPower || mel.n_mels <= kMaxMels, "%s: at most %d mel filters (got %d)", name, kMaxMels, mel.n_mels);
-  const size_t smem = sizeof(float) * (size_t)(kSlots * 4 * kBuf + kPieceTaps * kMaxPieces + kSlots * kMaxPieces +
-                                               2 * kMaxPieces + kMaxMels + 4 + (kFramesPerChunk - 1) * hop + kNfft);
-  auto kern = logmel_kernel<InT, kPower>;
-  static thread_local int configured_dev = -1;   // attribute is per (function, device)
-  int dev = 0;
-  SED_CUDA(cudaGetDevice(&dev));
-  if (configured_dev != dev) {
-    SED_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured_dev = dev;
-  }
-  SED_REQUIRE(smem <= 200 * 1024, "%s: hop %d needs %zu B of shared memory", name, hop, smem);
-  const long long items = (long long)n_clips * chunks;
-  const int per_sm = (int)max((size_t)1, min((size_t)3, (size_t)(220 * 1024) / smem));
+  const int n_frames = n_samples / hop + 1;
+  // consecutive frames of an item are walked by the four warps of one CTA (L1 serves their overlap); small inputs get
+  // small items so that every SM has work
+  const int per_sm = 3;
+  int fpi = kFramesPerChunk;
+  while (fpi > kWarpsW && (long long)n_clips * ceil_div(n_frames, fpi) < 2LL * sm_count() * per_sm) fpi >>= 1;
+  const int items_per_clip = ceil_div(n_frames, fpi);
+  const size_t smem = sizeof(float) * (size_t)(kPieceTaps * kMaxPieces + 2 * kMaxPieces + kMaxMels + 4 +
+                                               kWarpsW * (2 * 16 * kTS + kPLen + kMaxPieces));
+  // 8-byte (fp32) / 4-byte (int16) pair loads need an even clip length and an aligned base
+  const int pair_ok = (n_samples % 2 == 0 && aligned(wave, 2 * sizeof(InT))) ? 1 : 0;
+  auto kern = logmel_warp_kernel<InT, kPower>;
+  SED_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long items = (long long)n_clips * items_per_clip;
   const int grid = (int)min(items, (long long)sm_count() * per_sm);
-  kern<<<grid, kThreads, smem, stream>>>(wave, n_clips, n_samples, hop, n_frames, chunks, mel, out);
+  kern<<<grid, kThreadsW, smem, stream>>>(wave, n_clips, n_samples, hop, n_frames, fpi, items_per_clip, pair_ok, mel, out);
   SED_LAUNCH_CHECK(name);
   return 0;
 }
