@@ -223,8 +223,11 @@ int sed_colsum_f32(const float* x, long long rows, int C, float* partial, sed_st
  * bwd: carry = (2,2,B,H) scratch; writes dgx, dgh (B,T,2,3H) and hprev (B,T,2,H). */
 int sed_gru_fwd(const float* gx, const float* w_hh, const float* b_hh, float* out, float* gates, void* sync_ws,
                 int B, int T, int H, sed_stream_t stream);
+/* dgx_bf16 / dgh_bf16 / hprev_bf16: optional (all three or none, H = 256 only) bf16 copies of the three outputs,
+ * written by the same kernel: the operands of the weight-gradient GEMMs that follow (saves three conversion passes). */
 int sed_gru_bwd(const float* dout, const float* out, const float* gates, const float* w_hh, float* carry,
-                float* dgx, float* dgh, float* hprev, int B, int T, int H, sed_stream_t stream);
+                float* dgx, float* dgh, float* hprev, void* dgx_bf16, void* dgh_bf16, void* hprev_bf16, int B, int T,
+                int H, sed_stream_t stream);
 
 /* ---- scaled-dot-product attention of MultiHead (pytorch/models.py:596-608 inside :641-665) -------
  * q/k/v: fp32 (B*T, ld) row-major, head h in columns [h*64, h*64+64): the outputs of the w_qs / w_ks /

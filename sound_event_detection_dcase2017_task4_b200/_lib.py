@@ -72,7 +72,7 @@ SIGNATURES = {
     'sed_transpose_to_bf16': [P, I, I, P, P],
     'sed_colsum_f32': [P, L, I, P, P],
     'sed_gru_fwd': [P, P, P, P, P, P, I, I, I, P],
-    'sed_gru_bwd': [P, P, P, P, P, P, P, P, I, I, I, P],
+    'sed_gru_bwd': [P, P, P, P, P, P, P, P, P, P, P, I, I, I, P],
     'sed_attention_fwd': [P, P, P, I, I, I, I, I, I, I, F, F, U, U, P, P, P],
     'sed_attention_bwd': [P, P, P, I, I, I, I, I, I, I, F, F, U, U, P, P, P, P, P, P],
     'sed_dropout_relu_fwd': [P, L, F, U, U, P, P],

@@ -386,7 +386,8 @@ gru_fwd_persistent_kernel(const float* __restrict__ Gx, const float* __restrict_
 __global__ void __launch_bounds__(kPThreads, 1)
 gru_bwd_persistent_kernel(const float* __restrict__ dout, const float* __restrict__ out, const float* __restrict__ gates,
                           const float* __restrict__ Whh, float* __restrict__ dGx, float* dGh,
-                          float* __restrict__ Hprev, GruPersist q) {
+                          float* __restrict__ Hprev, __nv_bfloat16* __restrict__ dGx16, __nv_bfloat16* __restrict__ dGh16,
+                          __nv_bfloat16* __restrict__ Hprev16, GruPersist q) {
   extern __shared__ __align__(16) uint8_t smem_gru[];
   __nv_bfloat16* sDh = reinterpret_cast<__nv_bfloat16*>(smem_gru);      // [32][kLdG]  dGh rows of the group, hi
   __nv_bfloat16* sDl = sDh + kPB * kLdG;                                //             lo
@@ -450,6 +451,18 @@ gru_bwd_persistent_kernel(const float* __restrict__ dout, const float* __restric
         *reinterpret_cast<float2*>(gh + H) = make_float2(dzp[0], dzp[1]);
         *reinterpret_cast<float2*>(gh + 2 * H) = make_float2(dnr[0], dnr[1]);
         *reinterpret_cast<float2*>(Hprev + (bt * 2 + d) * H + j) = hp2;
+        if (dGx16) {      // bf16 copies for the weight-gradient GEMMs that follow (dW_ih = dGx^T X, dW_hh = dGh^T Hprev)
+          __nv_bfloat16* gx16 = dGx16 + (bt * 2 + d) * 3 * H + j;
+          __nv_bfloat16* gh16 = dGh16 + (bt * 2 + d) * 3 * H + j;
+          const uint32_t pr = pack_bf16x2(drp[0], drp[1]), pz = pack_bf16x2(dzp[0], dzp[1]);
+          *reinterpret_cast<uint32_t*>(gx16) = pr;
+          *reinterpret_cast<uint32_t*>(gx16 + H) = pz;
+          *reinterpret_cast<uint32_t*>(gx16 + 2 * H) = pack_bf16x2(dnp[0], dnp[1]);
+          *reinterpret_cast<uint32_t*>(gh16) = pr;
+          *reinterpret_cast<uint32_t*>(gh16 + H) = pz;
+          *reinterpret_cast<uint32_t*>(gh16 + 2 * H) = pack_bf16x2(dnr[0], dnr[1]);
+          *reinterpret_cast<uint32_t*>(Hprev16 + (bt * 2 + d) * H + j) = pack_bf16x2(hp2.x, hp2.y);
+        }
       }
     }
     if (bs == T - 1) break;                              // dh of the step before the first is not needed
@@ -591,8 +604,12 @@ int sed_gru_fwd(const float* gx, const float* w_hh, const float* b_hh, float* ou
 }
 
 int sed_gru_bwd(const float* dout, const float* out, const float* gates, const float* w_hh, float* carry /* (2,2,B,H) */,
-                float* dgx, float* dgh, float* hprev, int B, int T, int H, sed_stream_t stream) {
+                float* dgx, float* dgh, float* hprev, void* dgx_bf16, void* dgh_bf16, void* hprev_bf16, int B, int T, int H,
+                sed_stream_t stream) {
   SED_REQUIRE(dout && out && gates && w_hh && carry && dgx && dgh && hprev, "sed_gru_bwd: null pointer");
+  const bool want16 = dgx_bf16 || dgh_bf16 || hprev_bf16;
+  SED_REQUIRE(!want16 || (dgx_bf16 && dgh_bf16 && hprev_bf16 && H == kPH),
+              "sed_gru_bwd: the bf16 copies come all three or not at all, and only from the H = %d kernel", kPH);
   SED_REQUIRE(H % kHT == 0 && H % 4 == 0 && H <= 256, "sed_gru_bwd: hidden size %d unsupported", H);
   if (B == 0 || T == 0) return 0;
   if (H == kPH) {
@@ -602,7 +619,8 @@ int sed_gru_bwd(const float* dout, const float* out, const float* gates, const f
                                  reinterpret_cast<unsigned int*>(carry), (cudaStream_t)stream, [&](void** a) {
                                    a[0] = (void*)&dout; a[1] = (void*)&out; a[2] = (void*)&gates; a[3] = (void*)&w_hh;
                                    a[4] = (void*)&dgx; a[5] = (void*)&dgh; a[6] = (void*)&hprev;
-                                   return 7;
+                                   a[7] = (void*)&dgx_bf16; a[8] = (void*)&dgh_bf16; a[9] = (void*)&hprev_bf16;
+                                   return 10;
                                  });
   }
   const size_t smem = sizeof(float) * (size_t)(3 * H * kHT + kBT * 3 * H + kBT * kHT);

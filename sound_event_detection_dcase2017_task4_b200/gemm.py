@@ -46,10 +46,10 @@ def linear_x3(x2d_f32, w_f32, bias=None):
     return gemm_nt(split3(x2d_f32, 0), split3(w_f32, 1), bias)
 
 
-def gemm_tn(a_bf16, b_bf16, m, n, out, a_col=0, b_col=0, accumulate=False):
+def gemm_tn(a_bf16, b_bf16, m, n, out, a_col=0, b_col=0, accumulate=False, ldb=None):
     """out (m, n) fp32 = A[:, a_col:a_col+m]^T @ B[:, b_col:b_col+n]; A (R, lda), B (R, ldb) bf16."""
     r, lda = a_bf16.shape
-    ldb = b_bf16.shape[1]
+    ldb = b_bf16.shape[1] if ldb is None else ldb
     assert b_bf16.shape[0] == r and a_bf16.is_contiguous() and b_bf16.is_contiguous()
     with torch.cuda.device(a_bf16.device):
         splits = _lib.lib().sed_gemm_tn_tc_splits(r, m, n)

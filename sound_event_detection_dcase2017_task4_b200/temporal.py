@@ -12,7 +12,7 @@ F32 = torch.float32
 
 
 class GruCtx(object):
-    __slots__ = ('x2d', 'out', 'gates', 'shape')
+    __slots__ = ('x2d', 'x3', 'out', 'gates', 'shape')
 
 
 def _gru_cat(gru):
@@ -32,7 +32,8 @@ def gru_forward(gru, feat, keep):
         raise NotImplementedError('only the reference GRU configuration is implemented')
     w_ih, b_ih, w_hh, b_hh = _gru_cat(gru)
     x2d = feat.contiguous().view(b * t, c)
-    gx = gemm.linear_x3(x2d, w_ih, b_ih)                         # (B*T, 2*3H) fp32
+    x3 = gemm.split3(x2d, 0)                                     # bf16 (B*T, 3C) = [hi | lo | hi]
+    gx = gemm.gemm_nt(x3, gemm.split3(w_ih, 1), b_ih)            # (B*T, 2*3H) fp32, fp32-class accuracy
     out = torch.empty((b, t, 2 * h), dtype=F32, device=feat.device)
     gates = torch.empty((b, t, 2, 4, h), dtype=F32, device=feat.device)
     sync_ws = torch.empty(4 * ((b + 31) // 32) + 4, dtype=torch.int32, device=feat.device)
@@ -42,7 +43,7 @@ def gru_forward(gru, feat, keep):
     ctx = None
     if keep:
         ctx = GruCtx()
-        ctx.x2d, ctx.out, ctx.gates, ctx.shape = x2d, out, gates, (b, t, c, h)
+        ctx.x2d, ctx.x3, ctx.out, ctx.gates, ctx.shape = x2d, x3, out, gates, (b, t, c, h)
     return out, ctx
 
 
@@ -55,12 +56,21 @@ def gru_backward(gru, ctx, dout, grad_of):
     dgx = torch.empty((b * t, 2 * 3 * h), dtype=F32, device=dev)
     dgh = torch.empty((b * t, 2 * 3 * h), dtype=F32, device=dev)
     hprev = torch.empty((b * t, 2 * h), dtype=F32, device=dev)
+    from . import conv as tcconv
+    fused16 = h == 256                      # the persistent kernel also emits the bf16 operands of the GEMMs below
+    if fused16:
+        dgx16 = torch.empty(dgx.shape, dtype=torch.bfloat16, device=dev)
+        dgh16 = torch.empty(dgh.shape, dtype=torch.bfloat16, device=dev)
+        hp16 = torch.empty(hprev.shape, dtype=torch.bfloat16, device=dev)
     with torch.cuda.device(dev):
         call('sed_gru_bwd', dout.data_ptr(), ctx.out.data_ptr(), ctx.gates.data_ptr(), w_hh.data_ptr(),
-             carry.data_ptr(), dgx.data_ptr(), dgh.data_ptr(), hprev.data_ptr(), b, t, h, stream_of(dout))
-    from . import conv as tcconv
-    dgx16, dgh16 = tcconv.to_bf16(dgx), tcconv.to_bf16(dgh)
-    x16, hp16 = tcconv.to_bf16(ctx.x2d), tcconv.to_bf16(hprev)
+             carry.data_ptr(), dgx.data_ptr(), dgh.data_ptr(), hprev.data_ptr(),
+             dgx16.data_ptr() if fused16 else 0, dgh16.data_ptr() if fused16 else 0, hp16.data_ptr() if fused16 else 0,
+             b, t, h, stream_of(dout))
+    if not fused16:
+        dgx16, dgh16, hp16 = tcconv.to_bf16(dgx), tcconv.to_bf16(dgh), tcconv.to_bf16(hprev)
+    # X as bf16: the hi third of the [hi | lo | hi] split the forward projection already made (row stride 3 * C)
+    x16 = ctx.x3 if ctx.x3 is not None else tcconv.to_bf16(ctx.x2d)
     # weight gradients: dW_ih[d] = dGx_d^T X ; dW_hh[d] = dGh_d^T Hprev_d ; biases = column sums
     db_ih = torch.empty(2 * 3 * h, dtype=F32, device=dev)
     db_hh = torch.empty(2 * 3 * h, dtype=F32, device=dev)
@@ -69,7 +79,7 @@ def gru_backward(gru, ctx, dout, grad_of):
     for d, sfx in enumerate(('', '_reverse')):
         g = grad_of(getattr(gru, 'weight_ih_l0' + sfx))
         if g is not None:
-            gemm.gemm_tn(dgx16, x16, 3 * h, c, g, a_col=d * 3 * h)
+            gemm.gemm_tn(dgx16, x16, 3 * h, c, g, a_col=d * 3 * h, ldb=x16.shape[1])
         g = grad_of(getattr(gru, 'weight_hh_l0' + sfx))
         if g is not None:
             gemm.gemm_tn(dgh16, hp16, 3 * h, h, g, a_col=d * 3 * h, b_col=d * h)
