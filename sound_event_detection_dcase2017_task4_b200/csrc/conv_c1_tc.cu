@@ -180,7 +180,9 @@ conv_c1_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const C1Par
 // The CUDA-core version spent 1.12 ms (8 x 9 FMAs per pixel-octet, latency-bound at 25 % occupancy); this one is
 // bound by the single pass over dY.
 constexpr int kWgStages = 4;
-constexpr int kWgRows = 8;            // image rows per work item (x0 rows staged once per item)
+constexpr int kWgRows = 16;           // image rows per work item (x0 rows staged once per item)
+constexpr int kWgSxFloats = (kWgRows + 2) * (128 + 2);   // one sx buffer (W <= 128)
+constexpr int kWgPf = ((kWgRows + 2) * (128 + 2) + kC1Epi - 1) / kC1Epi;   // prefetch registers per builder thread (W = 128 worst case)
 
 struct C1WgParams {
   int B, H, W, bh;
@@ -265,20 +267,37 @@ conv_c1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const C1WgP
     const int grp = et >> 7, gt = et & 127;                        // builder group, thread (= pixel) within it
     int nblk = 0;                                                  // K blocks seen so far (all items of this CTA)
     bool any = false;
+    // The fp32 input rows of item n+1 are fetched into registers while the tiles of item n are built, and written to
+    // the OTHER sx buffer at the top of the next iteration: one barrier per item and no global-load latency between
+    // barriers (round 1 staged them synchronously: the builders -- and behind them the MMA and the TMA ring -- idled
+    // ~1 us per 1.5 us item, which is why the kernel sat at 0.5 of the HBM roofline).
+    float pf[kWgPf];
+    auto fetch = [&](int it) {
+      const int b = it / p.chunks, h0 = (it % p.chunks) * kWgRows;
+      const float* img = p.x0 + (long long)b * p.H * p.W;
+#pragma unroll
+      for (int q = 0; q < kWgPf; ++q) {
+        const int i = et + q * kC1Epi;
+        const int r = i / ldx, c = i - r * ldx;
+        const int h = h0 - 1 + r, w = c - 1;
+        pf[q] = (r < kWgRows + 2 && h >= 0 && h < p.H && w >= 0 && w < p.W) ? __ldg(img + (long long)h * p.W + w) : 0.f;
+      }
+    };
+    int cur = 0;
+    if ((int)blockIdx.x < p.items) fetch(blockIdx.x);
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-      const int b = item / p.chunks, h0 = (item % p.chunks) * kWgRows;
+      const int h0 = (item % p.chunks) * kWgRows;
       const int nr = min(kWgRows, p.H - h0);
       const int nkb = (nr + p.bh - 1) / p.bh;
-      asm volatile("bar.sync 1, %0;" ::"n"(kC1Epi) : "memory");    // previous item's readers are done with sx
-      {
-        const float* img = p.x0 + (long long)b * p.H * p.W;
-        for (int i = et; i < (kWgRows + 2) * ldx; i += kC1Epi) {
-          const int r = i / ldx, c = i - r * ldx;
-          const int h = h0 - 1 + r, w = c - 1;
-          sx[i] = (h >= 0 && h < p.H && w >= 0 && w < p.W) ? __ldg(img + (long long)h * p.W + w) : 0.f;
-        }
+      float* sxc = sx + cur * kWgSxFloats;
+#pragma unroll
+      for (int q = 0; q < kWgPf; ++q) {
+        const int i = et + q * kC1Epi;
+        if (i < (kWgRows + 2) * ldx) sxc[i] = pf[q];
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(kC1Epi) : "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kC1Epi) : "memory");    // sx[cur] is complete; sx[cur ^ 1] has no reader left
+      if (item + (int)gridDim.x < p.items) fetch(item + gridDim.x);
+      cur ^= 1;
       for (int kb = 0; kb < nkb; ++kb, ++nblk) {
         // the two 4-warp groups build alternate K blocks, so two tiles are under construction at any time
         if ((nblk & 1) == grp) {
@@ -287,7 +306,7 @@ conv_c1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const C1WgP
           mbar_wait(&empty_bar[st], ph ^ 1);
           uint8_t* tile = smem_b + st * 16384;
           const int r = kb * p.bh + gt / p.W, wq = gt % p.W;       // pixel row within the item, column
-          const float* c = sx + r * ldx + wq;                      // window top-left (staged row r <-> image row h0+r-1)
+          const float* c = sxc + r * ldx + wq;                     // window top-left (staged row r <-> image row h0+r-1)
           uint32_t hi[5], lo[5];
           float win[10];
 #pragma unroll
@@ -398,7 +417,7 @@ int sed_conv_c1_wgrad(const float* x, const void* dy, float* partial, int B, int
     const uint32_t box[4] = {64, (uint32_t)W, (uint32_t)p.bh, 1};
     if (int rc = tc::make_tmap_bf16(&tm, dy, 4, dims, strides, box, "conv_c1 wgrad dY map")) return rc;
   }
-  const size_t smem = (size_t)2 * kWgStages * 16384 + (size_t)(kWgRows + 2) * (W + 2) * sizeof(float) + 1024;
+  const size_t smem = (size_t)2 * kWgStages * 16384 + (size_t)2 * kWgSxFloats * sizeof(float) + 1024;
   SED_CUDA(cudaFuncSetAttribute(conv_c1_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // every one of the sed_conv_c1_grid() partial rows is written (CTAs without work write zeros)
   conv_c1_wgrad_tc_kernel<<<sed_conv_c1_grid(), kC1Threads, smem, (cudaStream_t)stream>>>(tm, p);
