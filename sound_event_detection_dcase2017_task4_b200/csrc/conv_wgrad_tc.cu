@@ -277,14 +277,29 @@ conv3x3_wgrad_kw_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __gri
         tcgen05_fence_after();
         const uint32_t sa = smem_u32(smem + stage * p.stage_bytes);
         const uint32_t sx = sa + 2 * kSlabBytes;
-#pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-          const uint32_t sxk = sx + (uint32_t)(kh * p.W) * 128u;      // halo tile starts at image row h0 - 1
+        if (kN == 64) {
+          // Cin = 64: the three kh taps are stacked in N.  The B operand is MN-major, i.e. consecutive 64-channel chunks
+          // of N sit LBO bytes apart -- and the X tile of tap kh is the SAME halo tile one image row (W * 128 B) further
+          // down.  With LBO = W * 128 one N = 192 instruction reads the dY slab ONCE for all three taps and fills the
+          // same three accumulators (columns kh * 64 ...) as three N = 64 instructions would: a third of the A-operand
+          // shared-memory reads.  (ncu r02: the N = 64 instructions kept the tensor pipe 56 % busy at 82 % L1/TEX.)
+          constexpr uint32_t idesc3 = umma_idesc_bf16(128, 192, 1, 1);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {                            // 128 pixels = 8 x K16
             const uint64_t da = umma_desc_sw128(sa + ks * 2048, a_lbo, 1024);
-            const uint64_t db = umma_desc_sw128(sxk + ks * 2048, x_slab_bytes, 1024);
-            umma_bf16(tmem_base + kh * kN, da, db, idesc, (kt > k_begin || ks > 0) ? 1u : 0u);
+            const uint64_t db = umma_desc_sw128(sx + ks * 2048, (uint32_t)p.W * 128u, 1024);
+            umma_bf16(tmem_base, da, db, idesc3, (kt > k_begin || ks > 0) ? 1u : 0u);
+          }
+        } else {
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            const uint32_t sxk = sx + (uint32_t)(kh * p.W) * 128u;    // halo tile starts at image row h0 - 1
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {                          // 128 pixels = 8 x K16
+              const uint64_t da = umma_desc_sw128(sa + ks * 2048, a_lbo, 1024);
+              const uint64_t db = umma_desc_sw128(sxk + ks * 2048, x_slab_bytes, 1024);
+              umma_bf16(tmem_base + kh * kN, da, db, idesc, (kt > k_begin || ks > 0) ? 1u : 0u);
+            }
           }
         }
         umma_commit(&empty_bar[stage]);
