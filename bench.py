@@ -361,7 +361,7 @@ def run_logmel(args):
             'e2e_int16': {'value': frames / ms_e2e16 / 1e3, 'unit': 'Mframes/s', 'ms_per_step': ms_e2e16 / args.steps,
                           'h2d_bytes_per_step': int(pcm_host.numel() * 2), 'd2h_bytes_per_step': int(out_host.numel() * 4)},
             'gpu_launches': launches, 'clocks': clock_info,
-            'roofline': {'kernel': 'logmel_kernel<float> (sed_logmel_f32)', 'bound': 'hbm', 'achieved': round(achieved, 1),
+            'roofline': {'kernel': 'logmel_warp_kernel<float> (sed_logmel_f32)', 'bound': 'hbm', 'achieved': round(achieved, 1),
                          'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': round(achieved / peaks['hbm_gbs'], 4),
                          'peak_source': peaks['source'] + ' hbm_gbs', 'bytes_per_launch': bytes_per_launch,
                          'avg_launch_ms': round(ms_launch, 4), 'traffic': profile_value('logmel_traffic.json')},
@@ -603,7 +603,9 @@ def run_ours(args):
                   'clips': b2, 'achieved_gbs': round(lm_bytes / lm_ms / 1e6, 1), 'hbm_peak_gbs': measured_peaks()['hbm_gbs'],
                   'hbm_frac': round(lm_bytes / lm_ms / 1e6 / measured_peaks()['hbm_gbs'], 4),
                   'bytes_per_clip': lm_bytes // b2,
-                  'note': 'fp32 in + fp32 log-mel out (SURVEY 8d); the kernel is shared-memory-bandwidth bound, not HBM bound'}
+                  'note': 'fp32 in + fp32 log-mel out (SURVEY 8d), timed right after the training steps (clocks under the power cap); '
+                          'the kernel is instruction-issue / latency bound, not HBM bound (profiles/r02_logmel_ncu.md); '
+                          '`bench.py --workload logmel` times it alone'}
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload
     cpu = None
