@@ -120,8 +120,11 @@ int sed_bn_finalize(const float* partial, int P, int C, double count, const floa
                     float eps, float momentum, float* running_mean, float* running_var,
                     long long* num_batches_tracked, float* scale, float* shift, float* save_mean,
                     float* save_invstd, sed_stream_t stream);
+/* eval mode: affine from the running statistics; save_mean / save_invstd (optional) receive the frozen statistics in
+ * the form the backward entry points take them */
 int sed_bn_eval_affine(const float* running_mean, const float* running_var, const float* gamma, const float* beta,
-                       float eps, int C, float* scale, float* shift, sed_stream_t stream);
+                       float eps, int C, float* scale, float* shift, float* save_mean, float* save_invstd,
+                       sed_stream_t stream);
 int sed_bn_relu_pool_fwd(const void* y, const float* scale, const float* shift, int B, int H, int W, int C, int ph,
                          int pw, void* out, int out_is_f32, sed_stream_t stream);
 /* Backward of the same stage in two passes over y (no saved activation other than y itself):
@@ -143,9 +146,11 @@ int sed_bn_relu_pool_bwd_reduce(const void* y, const void* dA, int grad_is_f32, 
 /* mean_for_gy: NULL when the second partial column holds sum(g*xhat) (sed_bn0_bwd_reduce); the layer's batch mean
  * when it holds sum(g*y) (sed_bn_relu_pool_bwd_reduce, sed_conv3x3_tc_dgrad_bnr):
  * sum(g*xhat) = invstd*(sum(g*y) - mean*sum(g)). */
+/* frozen_stats != 0: the statistics are constants (eval-mode BatchNorm under autograd): the batch-mean terms of the
+ * coefficients are zero, dY = gamma*invstd*g. */
 int sed_bn_bwd_finalize(const float* partial, int P, int C, double count, const float* gamma, const float* invstd,
-                        const float* mean_for_gy, float* dgamma, float* dbeta, int accumulate, float* coef,
-                        sed_stream_t stream);
+                        const float* mean_for_gy, float* dgamma, float* dbeta, int accumulate, int frozen_stats,
+                        float* coef, sed_stream_t stream);
 int sed_bn_relu_pool_bwd_apply(const void* y, const void* dA, int grad_is_f32, const float* scale, const float* shift,
                                const float* mean, const float* invstd, const float* coef, int B, int H, int W, int C,
                                int ph, int pw, void* dy, int* sched, sed_stream_t stream);

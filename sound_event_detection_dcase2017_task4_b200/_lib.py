@@ -38,13 +38,13 @@ SIGNATURES = {
     'sed_conv_unpack_wgrad': [P, I, L, I, I, P, I, P],
     'sed_f32_to_bf16': [P, P, L, P],
     'sed_bn_finalize': [P, I, I, D, P, P, F, F, P, P, P, P, P, P, P, P],
-    'sed_bn_eval_affine': [P, P, P, P, F, I, P, P, P],
+    'sed_bn_eval_affine': [P, P, P, P, F, I, P, P, P, P, P],
     'sed_bn_relu_pool_fwd': [P, P, P, I, I, I, I, I, I, P, I, P],
     'sed_bn_bwd_partials': [I, I, I, I, I, I],
     'sed_bn_bwd_workspace_rows': [I, I, I, I, I, I],
     'sed_bn_bwd_sched_words': [],
     'sed_bn_relu_pool_bwd_reduce': [P, P, I, P, P, I, I, I, I, I, I, P, P, P],
-    'sed_bn_bwd_finalize': [P, I, I, D, P, P, P, P, P, I, P, P],
+    'sed_bn_bwd_finalize': [P, I, I, D, P, P, P, P, P, I, I, P, P],
     'sed_bn_relu_pool_bwd_apply': [P, P, I, P, P, P, P, P, I, I, I, I, I, I, P, P, P],
     'sed_stat_partials': [],
     'sed_colstats_f32': [P, L, I, P, P],

@@ -22,6 +22,7 @@ class _ConvBlockFn(torch.autograd.Function):
         a2, l2 = engine._conv_layer(block.conv2, block.bn2, a1, ph, pw, training, True, keep)
         ctx.layers = (l1, l2) if keep else None
         ctx.cin = cin
+        ctx.frozen = not training
         return a2.permute(0, 3, 1, 2)                       # NCHW view of the fp32 NHWC result
 
     @staticmethod
@@ -40,7 +41,7 @@ class _ConvBlockFn(torch.autograd.Function):
         dx = None
         for lc in (l2, l1):
             dy = ops.bn_relu_pool_bwd(lc.y, dA, lc.st, lc.bn, lc.ph, lc.pw, grad_of(lc.bn.weight),
-                                      grad_of(lc.bn.bias))
+                                      grad_of(lc.bn.bias), frozen=ctx.frozen)
             gw = grad_of(lc.conv.weight)
             if lc.is_c1:
                 if gw is not None:
@@ -69,7 +70,8 @@ def conv_block_forward(block, input, pool_size=(2, 2), pool_type='avg'):
     if not input.is_cuda:
         raise RuntimeError('ConvBlock: CUDA tensor required (no CPU path in this package)')
     ph, pw = pool_size
-    keep = block.training and torch.is_grad_enabled()
+    keep = torch.is_grad_enabled() and (input.requires_grad or any(
+        p.requires_grad for p in (block.conv1.weight, block.conv2.weight, block.bn1.weight, block.bn2.weight)))
     return _ConvBlockFn.apply(block, input, ph, pw, keep, block.conv1.weight, block.conv2.weight, block.bn1.weight,
                               block.bn1.bias, block.bn2.weight, block.bn2.bias)
 

@@ -74,13 +74,16 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int P, int
 // eval mode: affine from the running statistics
 __global__ void bn_eval_affine_kernel(const float* __restrict__ running_mean, const float* __restrict__ running_var,
                                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                      int C, float* __restrict__ scale, float* __restrict__ shift) {
+                                      int C, float* __restrict__ scale, float* __restrict__ shift,
+                                      float* __restrict__ save_mean, float* __restrict__ save_invstd) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float invstd = 1.0f / sqrtf(running_var[c] + eps);
   const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
   scale[c] = g * invstd;
   shift[c] = b - running_mean[c] * g * invstd;
+  if (save_mean) save_mean[c] = running_mean[c];
+  if (save_invstd) save_invstd[c] = invstd;
 }
 
 // ---------------------------------------------------------------- forward
@@ -180,6 +183,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int P,
                                        const float* __restrict__ gamma, const float* __restrict__ invstd,
                                        const float* __restrict__ mean_for_gy,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
+                                       int frozen_stats,
                                        float* __restrict__ coef /* [3][C]: gamma*invstd, mean(g), mean(g*xhat) */) {
   const int c = blockIdx.x * 32 + threadIdx.x;
   double s, sx;
@@ -190,8 +194,9 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int P,
   if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)s : (float)s;
   if (coef) {
     coef[c] = (gamma ? gamma[c] : 1.f) * invstd[c];
-    coef[C + c] = (float)(s / count);
-    coef[2 * C + c] = (float)(sx / count);
+    // frozen (eval-mode) statistics are constants of the graph: dY = gamma * invstd * g, no batch terms
+    coef[C + c] = frozen_stats ? 0.f : (float)(s / count);
+    coef[2 * C + c] = frozen_stats ? 0.f : (float)(sx / count);
   }
 }
 
@@ -781,10 +786,11 @@ int sed_bn_finalize(const float* partial, int P, int C, double count, const floa
 }
 
 int sed_bn_eval_affine(const float* running_mean, const float* running_var, const float* gamma, const float* beta,
-                       float eps, int C, float* scale, float* shift, sed_stream_t stream) {
+                       float eps, int C, float* scale, float* shift, float* save_mean, float* save_invstd,
+                       sed_stream_t stream) {
   SED_REQUIRE(running_mean && running_var && scale && shift && C >= 1, "sed_bn_eval_affine: bad arguments");
   bn_eval_affine_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(running_mean, running_var, gamma, beta,
-                                                                            eps, C, scale, shift);
+                                                                            eps, C, scale, shift, save_mean, save_invstd);
   SED_LAUNCH_CHECK("bn_eval_affine_kernel");
   return 0;
 }
@@ -861,11 +867,12 @@ int sed_bn_relu_pool_bwd_reduce(const void* y, const void* dA, int grad_is_f32, 
 }
 
 int sed_bn_bwd_finalize(const float* partial, int P, int C, double count, const float* gamma, const float* invstd,
-                        const float* mean_for_gy, float* dgamma, float* dbeta, int accumulate, float* coef,
-                        sed_stream_t stream) {
+                        const float* mean_for_gy, float* dgamma, float* dbeta, int accumulate, int frozen_stats,
+                        float* coef, sed_stream_t stream) {
   SED_REQUIRE(partial && invstd && P >= 1 && C >= 1, "sed_bn_bwd_finalize: bad arguments");
   bn_bwd_finalize_kernel<<<ceil_div(C, 32), dim3(32, kColLanes), 0, (cudaStream_t)stream>>>(partial, P, C, count, gamma, invstd,
-                                                                             mean_for_gy, dgamma, dbeta, accumulate, coef);
+                                                                             mean_for_gy, dgamma, dbeta, accumulate,
+                                                                             frozen_stats, coef);
   SED_LAUNCH_CHECK("bn_bwd_finalize_kernel");
   return 0;
 }

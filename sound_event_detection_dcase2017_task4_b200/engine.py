@@ -158,7 +158,7 @@ def trunk_backward(ctx, dfeat, grad_of, overlap_wgrad=None):
     for li in range(len(ctx.layers) - 1, -1, -1):
         lc = ctx.layers[li]
         dy = ops.bn_relu_pool_bwd(lc.y, dA, lc.st, lc.bn, lc.ph, lc.pw, grad_of(lc.bn.weight),
-                                  grad_of(lc.bn.bias), gy_partial=gy_partial)
+                                  grad_of(lc.bn.bias), gy_partial=gy_partial, frozen=not ctx.training)
         gy_partial = None
         gw = grad_of(lc.conv.weight)
         side_wgrad = overlap_wgrad and gw is not None and not lc.is_c1 and li in OVERLAP_LAYERS

@@ -12,7 +12,8 @@ own forward is never called.  The whole forward runs inside ONE torch.autograd.F
 backward launches the hand-written backward kernels, so `loss.backward()` / `optimizer.step()`
 of the reference's main.py work unchanged.  Gradients flow to the parameters through
 ``clipwise_output`` only (that is what losses.clip_bce consumes); ``framewise_output`` and
-``embedding`` are returned detached.
+``embedding`` are returned detached.  Activations are kept whenever grad is enabled -- in eval()
+mode too, where the BatchNorm backward treats the running statistics as constants.
 """
 import math
 
@@ -188,8 +189,8 @@ class _SedFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dclip, _dframe, _demb):
         if ctx.saved is None:
-            raise RuntimeError('backward through a forward that kept no activations: the B200 path saves them only '
-                               'in train() mode with grad enabled (eval-mode forwards are inference-only)')
+            raise RuntimeError('backward through a forward that kept no activations (it ran under torch.no_grad() or '
+                               'was already backpropagated once)')
         tctx, mctx, hctx = ctx.saved
         ctx.saved = None
         grads = {}
@@ -257,7 +258,9 @@ class _Cnn9(nn.Module):
             raise RuntimeError('%s: CUDA tensors required -- this package has no CPU path'
                                % type(self).__name__)
         params = trainable_tensors(self)      # not self.parameters(): empty on DataParallel replicas
-        need_grad = self.training and torch.is_grad_enabled() and len(params) > 0
+        # activations are kept whenever a gradient can be asked for -- also in eval() mode (frozen-BatchNorm
+        # fine-tuning, saliency): the reference modules are differentiable there too
+        need_grad = torch.is_grad_enabled() and len(params) > 0
         clip, frame, emb = _SedFunction.apply(self, input, mixup_lambda, need_grad, *params)
         return {'framewise_output': frame, 'clipwise_output': clip, 'embedding': emb}
 

@@ -43,15 +43,17 @@ def bn_finalize(partial, count, bn, training_update=True):
 
 
 def bn_eval_affine(bn):
+    """Eval mode: scale / shift from the running statistics; mean / invstd are the frozen statistics (the backward
+    of an eval-mode forward under autograd treats them as constants)."""
     C = bn.num_features
     st = BNState()
-    buf = _empty((2, C), F32, bn.running_mean)
-    st.scale, st.shift = buf[0], buf[1]
-    st.mean = st.invstd = None
+    buf = _empty((4, C), F32, bn.running_mean)
+    st.scale, st.shift, st.mean, st.invstd = buf[0], buf[1], buf[2], buf[3]
     st.count = 0.0
     with _dev(buf):
         call('sed_bn_eval_affine', bn.running_mean.data_ptr(), bn.running_var.data_ptr(), ptr(bn.weight),
-             ptr(bn.bias), bn.eps, C, st.scale.data_ptr(), st.shift.data_ptr(), stream_of(buf))
+             ptr(bn.bias), bn.eps, C, st.scale.data_ptr(), st.shift.data_ptr(), st.mean.data_ptr(),
+             st.invstd.data_ptr(), stream_of(buf))
     return st
 
 
@@ -77,12 +79,13 @@ def sched_words(t):
     return w
 
 
-def bn_relu_pool_bwd(y, dA, st, bn, ph, pw, dgamma, dbeta, gy_partial=None):
+def bn_relu_pool_bwd(y, dA, st, bn, ph, pw, dgamma, dbeta, gy_partial=None, frozen=False):
     """Two-pass BN+ReLU+pool backward.  Writes bn parameter grads into dgamma/dbeta (fp32 (C,)
     tensors, may be None) and returns dY (bf16, same shape as y).
 
     ``gy_partial``: (P, 2, C) partial sums of g and g*y already produced by the data-gradient kernel that wrote
-    ``dA`` (conv.conv3x3_dgrad_bnr); the reduction pass over y and dA is then skipped."""
+    ``dA`` (conv.conv3x3_dgrad_bnr); the reduction pass over y and dA is then skipped.
+    ``frozen``: ``st`` holds running statistics (eval-mode forward): they are constants, dY = gamma * invstd * g."""
     b, h, w, c = y.shape
     f32 = 1 if dA.dtype == F32 else 0
     with _dev(y):
@@ -97,7 +100,8 @@ def bn_relu_pool_bwd(y, dA, st, bn, ph, pw, dgamma, dbeta, gy_partial=None):
         else:
             partial, P = gy_partial, gy_partial.shape[0]
         call('sed_bn_bwd_finalize', partial.data_ptr(), P, c, float(b * h * w), ptr(bn.weight),
-             st.invstd.data_ptr(), st.mean.data_ptr(), ptr(dgamma), ptr(dbeta), 0, coef.data_ptr(), s)
+             st.invstd.data_ptr(), st.mean.data_ptr(), ptr(dgamma), ptr(dbeta), 0, 1 if frozen else 0,
+             coef.data_ptr(), s)
         dy = _empty(y.shape, BF16, y)
         call('sed_bn_relu_pool_bwd_apply', y.data_ptr(), dA.data_ptr(), f32, st.scale.data_ptr(),
              st.shift.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(), coef.data_ptr(), b, h, w, c,
@@ -141,7 +145,7 @@ def bn0_bwd(dout, logmel, st, bn, t_stripes, f_stripes, lam, dgamma, dbeta):
              partial.data_ptr(), s)
         # bn0: d(gamma) = sum d*xhat, d(beta) = sum d  (no dX needed: the waveform takes no gradient)
         call('sed_bn_bwd_finalize', partial.data_ptr(), P, m, float(b2 * t), 0, st.invstd.data_ptr(), 0,
-             ptr(dgamma), ptr(dbeta), 0, 0, s)
+             ptr(dgamma), ptr(dbeta), 0, 0, 0, s)
 
 
 def spec_augment_(x, t_stripes, f_stripes):

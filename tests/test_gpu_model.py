@@ -228,3 +228,50 @@ def test_dataparallel_single_gpu_and_no_cpu_path():
     assert _rel(o['clipwise_output'].cpu(), o_ref['clipwise_output']) <= 1e-3
     with pytest.raises(RuntimeError, match='CUDA'):
         copy.deepcopy(mine).cpu()(torch.from_numpy(wave))
+
+
+@pytest.mark.parametrize('name', ['Cnn_9layers_Gru_FrameAtt', 'Cnn_9layers_FrameAvg'])
+def test_eval_mode_is_differentiable_like_the_reference(name):
+    """the reference modules are differentiable in eval() mode (frozen-BatchNorm fine-tuning, saliency):
+    running statistics are constants of the graph, no SpecAugment, no mixup.  Same gradient rule as the train step."""
+    from oracle import sed, bf16_emulation
+    from sound_event_detection_dcase2017_task4_b200 import losses
+    ref, mine = _pair(name)
+    g = torch.Generator().manual_seed(11)
+    sd = ref.state_dict()
+    for k in sd:                                         # running statistics away from (0, 1)
+        if k.endswith('running_mean') and 'bn_att' not in k:
+            sd[k] = sd[k] + 0.1 * torch.randn(sd[k].shape, generator=g)
+        if k.endswith('running_var') and 'bn_att' not in k:
+            sd[k] = sd[k] * (0.5 + torch.rand(sd[k].shape, generator=g))
+    ref.load_state_dict(sd)
+    mine.load_state_dict(sd)
+    emu = bf16_emulation.emulate_bf16_storage(copy.deepcopy(ref))
+    _, wave, target = sed.synthetic_batch(4, 32000, seed=77)
+    wave, target = torch.from_numpy(wave), torch.from_numpy(target)
+    grads = {}
+    for tag, m in (('ref', ref), ('emu', emu)):
+        m.eval()
+        o_m = m(wave)
+        sed.clip_bce(o_m, {'target': target}).backward()
+        grads[tag] = {k: p.grad for k, p in m.named_parameters()}
+        if tag == 'ref':
+            o_ref = o_m['clipwise_output'].detach()
+    mine.eval()
+    o = mine(wave.cuda())
+    assert o['clipwise_output'].requires_grad
+    losses.clip_bce(o, {'target': target.cuda()}).backward()
+    assert _rel(o['clipwise_output'].detach().cpu(), o_ref) <= 2e-3
+    assert int(mine.bn0.num_batches_tracked) == 0 and torch.equal(mine.bn0.running_mean.cpu(), sd['bn0.running_mean'])
+    for k, p in mine.named_parameters():
+        g_ref, g_emu = grads['ref'][k], grads['emu'][k]
+        if g_ref is None:
+            assert p.grad is None, k
+            continue
+        if k in ('att_block.att.bias',):
+            continue
+        a, b, e = p.grad.cpu().double().flatten(), g_ref.double().flatten(), g_emu.double().flatten()
+        err = (a - b).norm().item() / max(b.norm().item(), 1e-30)
+        band = (e - b).norm().item() / max(b.norm().item(), 1e-30)
+        cos = torch.dot(a, b).item() / max(a.norm().item() * b.norm().item(), 1e-30)
+        assert err <= max(3e-2, 2.0 * band + 2e-2) and cos >= 0.9, (k, err, band, cos)

@@ -103,7 +103,7 @@ def test_main_py_training_loop_body_call_for_call(tmp_path):
         torch.manual_seed(100 + iteration)
         out = ref(torch.Tensor(b['waveform']), lam)
         l_ref = sed.clip_bce(out, {'target': sed.mix_pairs(torch.Tensor(b['target']), lam)})
-        ref_losses.append(float(l_ref))
+        ref_losses.append(float(l_ref.detach()))
         opt_ref.zero_grad()
         l_ref.backward()
         opt_ref.step()
