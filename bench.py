@@ -444,7 +444,8 @@ def run_ours(args):
     torch.manual_seed(0)
     model = getattr(models, MODEL)(*CTOR).to(dev)
     model.train()
-    trainer = FusedTrainer(model, lr=1e-3, world_size=world)
+    use_graph = (world == 1 or args.graph) and not args.no_graph
+    trainer = FusedTrainer(model, lr=1e-3, world_size=world, use_graph=use_graph)
 
     pcm, target_np = synthetic_rank_batch(b2, rank)
     wave_host = torch.from_numpy((pcm / np.float32(32767.)).astype(np.float32)).pin_memory()
@@ -478,6 +479,8 @@ def run_ours(args):
             marks[i + 1].record()
         barrier()
         ms = marks[0].elapsed_time(marks[-1])
+        if trainer.use_graph:                              # replays do not pass through the C-ABI launch counter
+            n0 = _lib.launch_count() - steps * trainer.graph_launches
         if tag:
             d = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(steps))
             per_step[tag] = {'median_ms': round(statistics.median(d), 4), 'min_ms': round(d[0], 4), 'max_ms': round(d[-1], 4)}
@@ -547,6 +550,7 @@ def run_ours(args):
     from sound_event_detection_dcase2017_task4_b200 import engine as _engine
     _overlap_was = _engine.OVERLAP_WGRAD
     _engine.OVERLAP_WGRAD = False                        # serial schedule: every kernel timed alone on one stream
+    _graph_was, trainer.use_graph = trainer.use_graph, False   # eager launches: the per-call events need them
     for _ in range(reps):
         _lib.PROFILE = [] if rank == 0 else None
         step_resident()
@@ -558,6 +562,7 @@ def run_ours(args):
                 a[1] += e0.elapsed_time(e1)
         _lib.PROFILE = None
     _engine.OVERLAP_WGRAD = _overlap_was
+    trainer.use_graph = _graph_was
     if rank == 0:
         peaks = measured_peaks()
         total_ms = sum(v[1] for v in agg.values()) / reps
@@ -625,7 +630,9 @@ def run_ours(args):
             'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
             'train_samples_per_s': value / 2,
-            'config': train_config(MODEL, bs, world),
+            'config': dict(train_config(MODEL, bs, world),
+                           launch='CUDA graph replay, one graph per input-buffer set (%d kernels per step)' % trainer.graph_launches
+                           if trainer.use_graph else 'eager launches through the C ABI'),
             'per_step_ms': per_step,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e / args.steps,
                     'h2d_bytes_per_step': int(wave_host.numel() * 4 + target_host.numel() * 4 + b2 * 4),
@@ -658,6 +665,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=256, help='batch_size per GPU (raw clips = 2x under mixup)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--graph', action='store_true', help='replay the step from a CUDA graph also at N > 1 (default: N = 1 only)')
+    ap.add_argument('--no-graph', action='store_true', help='eager launches at N = 1 too')
     ap.add_argument('--model', default=MODEL, help='any of the seven Cnn_9layers_* classes (default: the metric\'s model)')
     ap.add_argument('--workload', default='train', choices=['train', 'logmel', 'eval'])
     args = ap.parse_args()

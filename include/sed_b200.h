@@ -200,10 +200,12 @@ int sed_head_att_bwd(const float* att_logit, const float* norm_att, const float*
 int sed_bce_fwd_bwd(const float* prob, const float* target, long long n, float grad_scale, float* loss, float* dprob,
                     sed_stream_t stream);
 
-/* ---- optimizer: optim.Adam(amsgrad=True).step() (pytorch/main.py:144-145, :258) ---------------- */
+/* ---- optimizer: optim.Adam(amsgrad=True).step() (pytorch/main.py:144-145, :258) ----------------
+ * bias_corr_dev: NULL, or two device floats {1 - beta1^t, sqrt(1 - beta2^t)} that override the values computed from
+ * `step` -- the launch can then be replayed from a CUDA graph with the step number supplied through memory. */
 int sed_adam_amsgrad(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq,
                      long long n, float lr, float beta1, float beta2, float eps, int step, float grad_scale,
-                     sed_stream_t stream);
+                     const float* bias_corr_dev, sed_stream_t stream);
 
 
 /* ---- plain tensor-core GEMMs on the conv pipelines (GRU / attention projections) ---------------

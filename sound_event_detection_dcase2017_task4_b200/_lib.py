@@ -79,7 +79,7 @@ SIGNATURES = {
     'sed_dropout_relu_bwd': [P, P, L, F, P, P],
     'sed_vad_count': [P, P, I, I, I, P, P, P, P, P, P, P, P],
     'sed_vad_fill': [P, P, I, I, I, P, P, P, P, P, P, P, P],
-    'sed_adam_amsgrad': [P, P, P, P, P, L, F, F, F, F, I, F, P],
+    'sed_adam_amsgrad': [P, P, P, P, P, L, F, F, F, F, I, F, P, P],
 }
 _RESTYPES = {
     'sed_last_error_string': ctypes.c_char_p,

@@ -13,7 +13,12 @@ namespace {
 
 __global__ void adam_amsgrad_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                     float* __restrict__ v, float* __restrict__ vmax, long long n, float lr, float b1,
-                                    float b2, float eps, float bc1, float bc2_sqrt, float grad_scale) {
+                                    float b2, float eps, float bc1, float bc2_sqrt, float grad_scale,
+                                    const float* __restrict__ bias_corr_dev) {
+  if (bias_corr_dev) {                       // step-dependent scalars from device memory (CUDA-graph replays)
+    bc1 = bias_corr_dev[0];
+    bc2_sqrt = bias_corr_dev[1];
+  }
   const float step_size = lr / bc1;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float gi = g[i] * grad_scale;
@@ -36,7 +41,7 @@ extern "C" {
 
 int sed_adam_amsgrad(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq,
                      long long n, float lr, float beta1, float beta2, float eps, int step, float grad_scale,
-                     sed_stream_t stream) {
+                     const float* bias_corr_dev, sed_stream_t stream) {
   SED_REQUIRE(param && grad && exp_avg && exp_avg_sq && max_exp_avg_sq, "sed_adam_amsgrad: null pointer");
   SED_REQUIRE(step >= 1 && n >= 0, "sed_adam_amsgrad: step must be >= 1");
   if (n == 0) return 0;
@@ -45,7 +50,7 @@ int sed_adam_amsgrad(float* param, const float* grad, float* exp_avg, float* exp
   const int grid = (int)min((n + 255) / 256, (long long)sm_count() * 8);
   adam_amsgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, max_exp_avg_sq, n, lr,
                                                               beta1, beta2, eps, (float)bc1, (float)sqrt(bc2),
-                                                              grad_scale);
+                                                              grad_scale, bias_corr_dev);
   SED_LAUNCH_CHECK("adam_amsgrad_kernel");
   return 0;
 }

@@ -301,8 +301,12 @@ def bce(prob, target, want_grad=True, grad_scale=1.0):
     return loss, dprob
 
 
-def adam_amsgrad_(param, grad, exp_avg, exp_avg_sq, max_exp_avg_sq, lr, beta1, beta2, eps, step, grad_scale=1.0):
+def adam_amsgrad_(param, grad, exp_avg, exp_avg_sq, max_exp_avg_sq, lr, beta1, beta2, eps, step, grad_scale=1.0,
+                  bias_corr=None):
+    """``bias_corr``: optional device tensor of two floats (1 - beta1^t, sqrt(1 - beta2^t)) read by the kernel instead
+    of the values derived from ``step`` (CUDA-graph replays)."""
     n = param.numel()
     with _dev(param):
         call('sed_adam_amsgrad', param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
-             max_exp_avg_sq.data_ptr(), n, lr, beta1, beta2, eps, step, float(grad_scale), stream_of(param))
+             max_exp_avg_sq.data_ptr(), n, lr, beta1, beta2, eps, step, float(grad_scale), ptr(bias_corr),
+             stream_of(param))

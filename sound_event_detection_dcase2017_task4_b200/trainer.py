@@ -17,6 +17,8 @@ sequenced as libsedb200 launches on torch's current stream (engine.py / temporal
 The module classes in models.py give the same arithmetic through torch.autograd for the
 reference's unmodified main.py; this class is what bench.py times.
 """
+import math
+
 import torch
 
 from . import engine
@@ -43,7 +45,7 @@ def exchange_gradients(flat_grad, world_size, group=None):
 
 
 class FusedTrainer(object):
-    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, process_group=None, world_size=1):
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, process_group=None, world_size=1, use_graph=False):
         self.model = model
         self.lr, self.betas, self.eps = lr, betas, eps
         self.world_size = world_size
@@ -67,6 +69,15 @@ class FusedTrainer(object):
             self._grad[p] = self.flat_grad[off:off + n].view(p.shape)
             off += n
         self.step_count = 0
+        # Optional CUDA-graph replay of the step (single process, models without device-side dropout): one graph per
+        # set of input buffers; the per-step host inputs (SpecAugment stripes, Adam bias corrections) go through small
+        # static device tensors that are refreshed before every replay.
+        # (the multi-head models draw their dropout offsets on the host per step: they stay on eager launches)
+        self.use_graph = bool(use_graph) and getattr(model, 'temporal_kind', None) != 'mha'
+        self._graphs = {}
+        self._pool = None
+        self._eager_steps = 0
+        self.graph_launches = 0           # libsedb200 launches captured in one graph (bench.py: gpu_launches)
 
     def grad_of(self, p):
         if p is None or not p.requires_grad:
@@ -75,10 +86,17 @@ class FusedTrainer(object):
 
     def step(self, wave, target, lam):
         """wave (B2, L) fp32/int16, target (B2, K) fp32, lam (B2,) fp32 or None (all CUDA).
-        Returns the rank-local loss as a 0-d CUDA tensor (no host sync here)."""
+        Returns the rank-local loss as a 0-d CUDA tensor (no host sync here).  In graph mode the returned tensor is
+        a static buffer of the graph: read it before the next step."""
+        if self.use_graph and self._eager_steps >= 2:
+            return self._step_graph(wave, target, lam)
+        self._eager_steps += 1
+        return self._step_body(wave, target, lam)
+
+    def _step_body(self, wave, target, lam, stripes=None, bias_corr=None):
         model = self.model
         with torch.no_grad():
-            feat, tctx = engine.trunk_forward(model, wave, lam, True)
+            feat, tctx = engine.trunk_forward(model, wave, lam, True, stripes=stripes)
             feat, mctx = temporal.forward(model, feat, True, keep=True)
             out, hctx = engine.head_forward(model, feat, model.interpolate_ratio, want_frame=True, keep=True)
             tgt = ops.mix_pairs(target, lam) if lam is not None else target
@@ -91,6 +109,48 @@ class FusedTrainer(object):
             self.step_count += 1
             ops.adam_amsgrad_(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq,
                               self.max_exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps,
-                              self.step_count)
+                              self.step_count, bias_corr=bias_corr)
         self.last_output = out
         return loss
+
+    def _step_graph(self, wave, target, lam):
+        from . import _lib, specaug
+        import numpy as np
+        model = self.model
+        dev = self.flat_param.device
+        b2, n = wave.shape
+        key = (wave.data_ptr(), target.data_ptr(), 0 if lam is None else lam.data_ptr(), tuple(wave.shape), wave.dtype)
+        aug = model.spec_augmenter
+        hop = model.spectrogram_extractor.stft.hop_length
+        t, m = n // hop + 1, model.bn0.num_features
+        ts, fs = specaug.draw_spec_augment(b2, t, m, aug.time_dropper.drop_width, aug.time_dropper.stripes_num,
+                                           aug.freq_dropper.drop_width, aug.freq_dropper.stripes_num)
+        step = self.step_count + 1
+        b1, b2 = float(np.float32(self.betas[0])), float(np.float32(self.betas[1]))   # the C ABI takes the betas as float
+        bc = np.array([1.0 - math.pow(b1, step), math.sqrt(1.0 - math.pow(b2, step))],
+                      dtype=np.float32)                  # the doubles csrc/adam.cu computes, rounded to float like there
+        entry = self._graphs.get(key)
+        if entry is None:
+            entry = {'ts': torch.empty(ts.shape, dtype=torch.int32, device=dev),
+                     'fs': torch.empty(fs.shape, dtype=torch.int32, device=dev),
+                     'bc': torch.empty(2, dtype=torch.float32, device=dev)}
+        # pageable -> device copies are staged by the driver before the call returns: the host arrays may be reused
+        entry['ts'].copy_(torch.from_numpy(ts))
+        entry['fs'].copy_(torch.from_numpy(fs))
+        entry['bc'].copy_(torch.from_numpy(bc))
+        if 'graph' not in entry:
+            n0 = _lib.launch_count()
+            count0 = self.step_count
+            g = torch.cuda.CUDAGraph()
+            if self._pool is None:
+                self._pool = torch.cuda.graph_pool_handle()   # all graphs of this trainer share one memory pool: they
+            with torch.cuda.graph(g, pool=self._pool):        # are replayed one at a time and their outputs are read first
+                loss = self._step_body(wave, target, lam, stripes=(entry['ts'], entry['fs']), bias_corr=entry['bc'])
+            self.step_count = count0                       # capture executed nothing
+            entry['graph'], entry['loss'], entry['out'] = g, loss, self.last_output
+            self.graph_launches = _lib.launch_count() - n0
+            self._graphs[key] = entry
+        entry['graph'].replay()
+        self.step_count += 1
+        self.last_output = entry['out']
+        return entry['loss']
