@@ -444,7 +444,7 @@ def run_ours(args):
     torch.manual_seed(0)
     model = getattr(models, MODEL)(*CTOR).to(dev)
     model.train()
-    use_graph = (world == 1 or args.graph) and not args.no_graph
+    use_graph = world == 1 and not args.no_graph
     trainer = FusedTrainer(model, lr=1e-3, world_size=world, use_graph=use_graph)
 
     pcm, target_np = synthetic_rank_batch(b2, rank)
@@ -665,8 +665,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=256, help='batch_size per GPU (raw clips = 2x under mixup)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--graph', action='store_true', help='replay the step from a CUDA graph also at N > 1 (default: N = 1 only)')
-    ap.add_argument('--no-graph', action='store_true', help='eager launches at N = 1 too')
+    ap.add_argument('--no-graph', action='store_true', help='eager launches instead of the CUDA-graph replay used at N = 1')
     ap.add_argument('--model', default=MODEL, help='any of the seven Cnn_9layers_* classes (default: the metric\'s model)')
     ap.add_argument('--workload', default='train', choices=['train', 'logmel', 'eval'])
     args = ap.parse_args()

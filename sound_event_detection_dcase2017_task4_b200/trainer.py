@@ -72,8 +72,9 @@ class FusedTrainer(object):
         # Optional CUDA-graph replay of the step (single process, models without device-side dropout): one graph per
         # set of input buffers; the per-step host inputs (SpecAugment stripes, Adam bias corrections) go through small
         # static device tensors that are refreshed before every replay.
-        # (the multi-head models draw their dropout offsets on the host per step: they stay on eager launches)
-        self.use_graph = bool(use_graph) and getattr(model, 'temporal_kind', None) != 'mha'
+        # (the multi-head models draw their dropout offsets on the host per step, and capturing the NCCL all-reduce
+        #  inside the two-stream graph hung in a 2-GPU trial: both stay on eager launches)
+        self.use_graph = bool(use_graph) and world_size == 1 and getattr(model, 'temporal_kind', None) != 'mha'
         self._graphs = {}
         self._pool = None
         self._eager_steps = 0
