@@ -69,12 +69,13 @@ class FusedTrainer(object):
             self._grad[p] = self.flat_grad[off:off + n].view(p.shape)
             off += n
         self.step_count = 0
-        # Optional CUDA-graph replay of the step (single process, models without device-side dropout): one graph per
-        # set of input buffers; the per-step host inputs (SpecAugment stripes, Adam bias corrections) go through small
-        # static device tensors that are refreshed before every replay.
-        # (the multi-head models draw their dropout offsets on the host per step, and capturing the NCCL all-reduce
-        #  inside the two-stream graph hung in a 2-GPU trial: both stay on eager launches)
-        self.use_graph = bool(use_graph) and world_size == 1 and getattr(model, 'temporal_kind', None) != 'mha'
+        # Optional CUDA-graph replay of the step (models without device-side dropout): one graph per set of input
+        # buffers; the per-step host inputs (SpecAugment stripes, Adam bias corrections) go through small static device
+        # tensors that are refreshed before every replay.  With world_size > 1 the graph ends before the collective
+        # (capturing the NCCL all-reduce inside the two-stream graph hung in a 2-GPU trial): forward + backward replay
+        # as one graph, then the all-reduce and the one Adam kernel are launched eagerly.
+        # (the multi-head models draw their dropout offsets on the host per step and stay on eager launches)
+        self.use_graph = bool(use_graph) and getattr(model, 'temporal_kind', None) != 'mha'
         self._graphs = {}
         self._pool = None
         self._eager_steps = 0
@@ -95,6 +96,20 @@ class FusedTrainer(object):
         return self._step_body(wave, target, lam)
 
     def _step_body(self, wave, target, lam, stripes=None, bias_corr=None):
+        loss = self._forward_backward(wave, target, lam, stripes)
+        self._update(bias_corr)
+        return loss
+
+    def _update(self, bias_corr=None):
+        """The collective and the optimizer: all-reduce of the flat gradient, then Adam(amsgrad) over the flat buffers."""
+        with torch.no_grad():
+            exchange_gradients(self.flat_grad, self.world_size, self.group)
+            self.step_count += 1
+            ops.adam_amsgrad_(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq,
+                              self.max_exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps,
+                              self.step_count, bias_corr=bias_corr)
+
+    def _forward_backward(self, wave, target, lam, stripes=None):
         model = self.model
         with torch.no_grad():
             feat, tctx = engine.trunk_forward(model, wave, lam, True, stripes=stripes)
@@ -106,11 +121,6 @@ class FusedTrainer(object):
             dfeat = engine.head_backward(model, hctx, dprob, self.grad_of)
             dfeat = temporal.backward(model, mctx, dfeat, self.grad_of)
             engine.trunk_backward(tctx, dfeat, self.grad_of)
-            exchange_gradients(self.flat_grad, self.world_size, self.group)
-            self.step_count += 1
-            ops.adam_amsgrad_(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq,
-                              self.max_exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps,
-                              self.step_count, bias_corr=bias_corr)
         self.last_output = out
         return loss
 
@@ -146,12 +156,18 @@ class FusedTrainer(object):
             if self._pool is None:
                 self._pool = torch.cuda.graph_pool_handle()   # all graphs of this trainer share one memory pool: they
             with torch.cuda.graph(g, pool=self._pool):        # are replayed one at a time and their outputs are read first
-                loss = self._step_body(wave, target, lam, stripes=(entry['ts'], entry['fs']), bias_corr=entry['bc'])
+                if self.world_size == 1:
+                    loss = self._step_body(wave, target, lam, stripes=(entry['ts'], entry['fs']), bias_corr=entry['bc'])
+                else:
+                    loss = self._forward_backward(wave, target, lam, stripes=(entry['ts'], entry['fs']))
             self.step_count = count0                       # capture executed nothing
             entry['graph'], entry['loss'], entry['out'] = g, loss, self.last_output
             self.graph_launches = _lib.launch_count() - n0
             self._graphs[key] = entry
         entry['graph'].replay()
-        self.step_count += 1
+        if self.world_size == 1:
+            self.step_count += 1
+        else:
+            self._update()
         self.last_output = entry['out']
         return entry['loss']

@@ -1,6 +1,8 @@
 """Worker of the world-size-2 tests (tests/test_gpu_reference_loop.py, tests/test_host_logic.py): one process per
 rank, gloo rendezvous on 127.0.0.1.  mode 'cpu': only the gradient exchange + sharding helpers (no CUDA).  mode
-'gpu': both ranks share cuda:0 and run one FusedTrainer step on their shard of a common synthetic batch."""
+'gpu': both ranks share cuda:0 and run one FusedTrainer step on their shard of a common synthetic batch.  modes
+'gpu4' / 'gpu4_graph': four steps on the same device buffers, eager / with the CUDA-graph replay of forward + backward
+(the all-reduce and Adam stay eager at world size > 1)."""
 import os
 import sys
 
@@ -34,15 +36,20 @@ def main():
         model = getattr(models, name)(32000, 1024, 320, 64, 50, 14000, 17).cuda().train()
         for m in (model.spec_augmenter.time_dropper, model.spec_augmenter.freq_dropper):
             m.drop_width = 1                                               # zero-width stripes: ranks draw independently
-        trainer = tr.FusedTrainer(model, lr=1e-3, world_size=world)
+        trainer = tr.FusedTrainer(model, lr=1e-3, world_size=world, use_graph=(mode == 'gpu4_graph'))
         _, wave, target = sed.synthetic_batch(16, 32000, seed=77)
         lam = sed.MixupLambda(1., 1234).get_lambda(16).astype(np.float32)
         lo, hi = tr.shard_bounds(16, world, rank)
-        loss = trainer.step(torch.from_numpy(wave[lo:hi]).cuda(), torch.from_numpy(target[lo:hi]).cuda(),
-                            torch.from_numpy(lam[lo:hi]).cuda())
+        dev_in = (torch.from_numpy(wave[lo:hi]).cuda(), torch.from_numpy(target[lo:hi]).cuda(),
+                  torch.from_numpy(lam[lo:hi]).cuda())
+        losses = []
+        for _ in range(1 if mode == 'gpu' else 4):
+            loss = trainer.step(*dev_in)
+            losses.append(float(loss))                                     # read before the next replay overwrites it
         torch.cuda.synchronize()
-        torch.save({'loss': float(loss), 'grad': trainer.flat_grad.cpu(), 'param': trainer.flat_param.cpu(),
-                    'bounds': (lo, hi)}, os.path.join(out_dir, 'rank%d.pt' % rank))
+        torch.save({'loss': losses[0], 'losses': losses, 'grad': trainer.flat_grad.cpu(),
+                    'param': trainer.flat_param.cpu(), 'bounds': (lo, hi), 'graphs': len(trainer._graphs),
+                    'steps': trainer.step_count}, os.path.join(out_dir, 'rank%d.pt' % rank))
     dist.barrier()
     dist.destroy_process_group()
 

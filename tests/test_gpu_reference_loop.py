@@ -326,3 +326,20 @@ def test_forward_inference_loop_matches_the_oracle_loop(tmp_path):
     assert np.array_equal(out16['framewise_output'], out['framewise_output'])
     assert out16['waveform'].dtype == np.int16 and out16['waveform'].shape == (7, 32000)
     assert np.array_equal(pu.pad_framewise_output(out['framewise_output'], 50), out['framewise_output'][:, :50])
+
+
+@pytest.mark.gpu
+def test_two_rank_graph_replay_equals_two_rank_eager(tmp_path, run_two_ranks):
+    """World size 2 with ``use_graph=True``: forward + backward replay as one CUDA graph per rank, the all-reduce and
+    the Adam kernel follow as eager launches (trainer.FusedTrainer).  Four steps must leave bit-identical parameters,
+    gradients and losses to four eager steps, on both ranks."""
+    (tmp_path / 'eager').mkdir()
+    (tmp_path / 'graph').mkdir()
+    e0, e1 = run_two_ranks('gpu4', tmp_path / 'eager')
+    g0, g1 = run_two_ranks('gpu4_graph', tmp_path / 'graph')
+    assert g0['graphs'] == 1 and g1['graphs'] == 1 and e0['graphs'] == 0
+    assert g0['steps'] == 4 and e0['steps'] == 4
+    for e, g in ((e0, g0), (e1, g1)):
+        assert e['losses'] == g['losses']
+        assert torch.equal(e['grad'], g['grad']) and torch.equal(e['param'], g['param'])
+    assert torch.equal(g0['param'], g1['param'])
