@@ -46,6 +46,20 @@ def test_logmel_int16_input_equals_float_path():
     assert torch.equal(a, b)            # x/32767 fused into the gather is bit-identical
 
 
+def test_int16_conversion_on_device_equals_reference_for_every_value():
+    """Every int16 value goes through the kernel's x/32767 (csrc/logmel.cu Sample<int16_t>::cvt, a multiply + two
+    FMAs): the log-mel of PCM input is bit-identical to that of the reference-converted fp32 waveform
+    (utils/utilities.py:66-67) on clips that contain all 65536 values, in order and shuffled."""
+    from sound_event_detection_dcase2017_task4_b200 import frontend as fe
+    allv = np.arange(-32768, 32768, dtype=np.int32).astype(np.int16)
+    rs = np.random.RandomState(3)
+    pcm = np.stack([allv, rs.permutation(allv), allv[::-1].copy()])
+    wave = (pcm / 32767.).astype(np.float32)
+    a = fe.logmel(torch.from_numpy(wave).cuda(), 320, _bank('cuda'))
+    b = fe.logmel(torch.from_numpy(pcm).cuda(), 320, _bank('cuda'))
+    assert torch.equal(a, b)
+
+
 def test_logmel_gaussian_input():
     from sound_event_detection_dcase2017_task4_b200 import frontend as fe
     rs = np.random.RandomState(5)

@@ -43,6 +43,43 @@ def test_int16_fp32_division_matches_reference_conversion():
     assert np.array_equal(ref, dev)
 
 
+def _round_to_f32(fr):
+    """Fraction -> nearest float32, ties to even (normal range): exact, no double rounding."""
+    import math
+    from fractions import Fraction
+    if fr == 0:
+        return np.float32(0)
+    a = abs(fr)
+    e = math.floor(math.log2(a))
+    while Fraction(2) ** e > a:
+        e -= 1
+    while Fraction(2) ** (e + 1) <= a:
+        e += 1
+    ulp = Fraction(2) ** (e - 23)
+    n = a / ulp
+    lo = n.numerator // n.denominator
+    rem = n - lo
+    if rem > Fraction(1, 2) or (rem == Fraction(1, 2) and lo % 2 == 1):
+        lo += 1
+    return np.float32((-1 if fr < 0 else 1) * float(lo * ulp))
+
+
+def test_int16_fma_quotient_is_the_correctly_rounded_division():
+    """csrc/logmel.cu Sample<int16_t>::cvt replaces the IEEE division by q0 = v * r, e = fma(-q0, 32767, v),
+    q = fma(e, r, q0) with r = fl(1 / 32767).  Replayed here in exact rational arithmetic with one rounding per
+    instruction: it equals the reference conversion (utils/utilities.py:66-67) for every int16 value."""
+    from fractions import Fraction
+    r = _round_to_f32(Fraction(1, 32767))
+    assert r == np.float32(1.0) / np.float32(32767.0)
+    fr = Fraction(float(r))
+    pcm = np.arange(-32768, 32768, dtype=np.int64)
+    ref = (pcm / 32767.).astype(np.float32)
+    for v, want in zip(pcm.tolist(), ref):
+        q0 = Fraction(float(_round_to_f32(Fraction(v) * fr)))
+        e = Fraction(float(_round_to_f32(Fraction(v) - q0 * 32767)))
+        assert _round_to_f32(e * fr + q0) == want, v
+
+
 def test_specaug_replay_is_bit_exact_and_advances_generator():
     from oracle import frontend as ofe
     from sound_event_detection_dcase2017_task4_b200 import specaug
