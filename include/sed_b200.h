@@ -225,9 +225,12 @@ int sed_colsum_f32(const float* x, long long rows, int C, float* partial, sed_st
 /* ---- bidirectional GRU recurrence: nn.GRU(512, 256, bidirectional) (pytorch/models.py:437-438,
  * :529-530; calls :475, :566).  gx = x W_ih^T + b_ih for both directions (B,T,2,3H), gate order
  * r,z,n; w_hh (2,3H,H), b_hh (2,3H); out (B,T,2H); gates (B,T,2,4,H) saved for the backward.
- * sync_ws: >= 16 * ceil(B/32) bytes of scratch for the persistent kernel's group counters (H = 256; the
- * entry point zeroes it on the stream); NULL selects the per-step kernels.
- * bwd: carry = (2,2,B,H) scratch; writes dgx, dgh (B,T,2,3H) and hprev (B,T,2,H). */
+ * sync_ws: sed_gru_workspace_bytes(B, H, 0) bytes of 16-byte-aligned scratch: the exchange area of the persistent
+ * kernel (H = 256: the group's h rows of each step travel through it as flagged 8-byte words; the entry point zeroes it
+ * on the stream); NULL selects the per-step kernels.
+ * bwd: carry = sed_gru_workspace_bytes(B, H, 1) bytes of 16-byte-aligned scratch (the (2,2,B,H) carry of the per-step
+ * kernels, or the dGh exchange area of the persistent one); writes dgx, dgh (B,T,2,3H) and hprev (B,T,2,H). */
+long long sed_gru_workspace_bytes(int B, int H, int backward);
 int sed_gru_fwd(const float* gx, const float* w_hh, const float* b_hh, float* out, float* gates, void* sync_ws,
                 int B, int T, int H, sed_stream_t stream);
 /* dgx_bf16 / dgh_bf16 / hprev_bf16: optional (all three or none, H = 256 only) bf16 copies of the three outputs,

@@ -71,6 +71,7 @@ SIGNATURES = {
     'sed_split_bf16x3': [P, L, I, I, P, P],
     'sed_transpose_to_bf16': [P, I, I, P, P],
     'sed_colsum_f32': [P, L, I, P, P],
+    'sed_gru_workspace_bytes': [I, I, I],
     'sed_gru_fwd': [P, P, P, P, P, P, I, I, I, P],
     'sed_gru_bwd': [P, P, P, P, P, P, P, P, P, P, P, I, I, I, P],
     'sed_attention_fwd': [P, P, P, I, I, I, I, I, I, I, F, F, U, U, P, P, P],
@@ -84,6 +85,7 @@ SIGNATURES = {
 _RESTYPES = {
     'sed_last_error_string': ctypes.c_char_p,
     'sed_launch_count': ctypes.c_ulonglong,
+    'sed_gru_workspace_bytes': ctypes.c_longlong,
 }
 
 _lock = threading.Lock()

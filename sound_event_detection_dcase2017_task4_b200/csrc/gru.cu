@@ -153,43 +153,50 @@ gru_bwd_step_kernel(const float* __restrict__ dout, const float* __restrict__ ou
 // x 125 steps) and pay a launch per step.  For the reference configuration (hidden size 256) the whole
 // recurrence instead runs in ONE cooperative launch: a group of 8 CTAs owns (32 batch rows, one direction);
 // CTA r of the group keeps the slice of W_hh for hidden units [32r, 32r+32) in shared memory for all T
-// steps.  The groups exchange one time step through L2 (the `out` / `dGh` tensors that have to be written
-// anyway) and meet at a per-group arrive/wait counter in global memory.  (A thread-block-cluster version
-// with DSMEM exchange was measured first: only 8 clusters of 8 CTAs x 164 KB are co-resident on a B200, which
-// leaves more than half of the SMs idle -- profiles/r01_gru_cluster.md -- so the group barrier lives in L2.)
-// Accumulation order per output is the same as in the step kernels (bit-identical forward results).
+// steps.  (A thread-block-cluster version with DSMEM exchange was measured first: only 8 clusters of 8 CTAs x 164 KB
+// are co-resident on a B200, which leaves more than half of the SMs idle -- profiles/r01_gru_cluster.md -- so the
+// exchange goes through L2.)
+//
+// Per-step exchange (round 2): flagged 8-byte words, no barrier.  Round 1 met at a counter in global memory (bar.sync,
+// __threadfence, atomicAdd, acquire-poll, bar.sync) and then read the step's rows back from the output tensor: ncu
+// (profiles/r02_gru_ncu.md) put 39 % of all warp time into that meeting -- 1.25 us per step in the fence alone, which
+// has to wait for the 10 KB of gate / output stores in front of it, 0.6 us in the L1-invalidating acquire polls.  Now
+// every produced value travels as {bf16 hi | bf16 lo, tag} in one 8-byte word of a double-buffered exchange area
+// (tag = step + 1, area zeroed by the host entry point): a consumer polls the words it needs until their tags match
+// and has data and "ready" in the same L2 round trip -- no fence, no atomic, and the hi/lo split the tensor-core
+// product needs is made once by the producer instead of by all 8 consumers.  8-byte accesses are single transactions;
+// the 16-byte vector accesses used here carry two such words and both tags are checked.
+// Slot reuse: slot (s & 1) is rewritten at step s + 2, which a producer only reaches after it has consumed step s + 1
+// from all 8 CTAs, and each of those wrote its step s + 1 values after all of its threads had finished reading step s.
+// The two 16-row halves of a CTA own disjoint batch rows, i.e. independent recurrences: while one half polls, the
+// other computes.
 constexpr int kPH = 256;           // hidden size handled by the persistent kernels
 constexpr int kPB = 32;            // batch rows per group
 constexpr int kPJ = 32;            // hidden units per CTA
 constexpr int kPGroup = kPH / kPJ; // 8 CTAs per group
 constexpr int kPThreads = 256;
 
-// Group barrier for one 16-row half of a CTA (4 warps, named barrier `bar_id`): all 8 CTAs of the group arrive on the
-// half's counter; everyone leaves once `target` arrivals have been counted.  Writes made by any thread of the half
-// before the call are visible to every thread of the group's halves after it (bar.sync, then the leader thread:
-// fence + atomic + acquire spin, then bar.sync -- the cooperative-groups grid.sync pattern).  The two halves of a
-// CTA own disjoint batch rows, i.e. independent recurrences, and use separate counters: while one half waits for its
-// barrier the other one computes, which hides most of the per-step exchange latency.
 __device__ __forceinline__ void half_barrier_sync(int bar_id) {
   asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 }
-__device__ __forceinline__ void group_barrier_half(unsigned int* ctr, unsigned int target, int bar_id, bool leader) {
-  half_barrier_sync(bar_id);
-  if (leader) {
-    __threadfence();
-    atomicAdd(ctr, 1u);
-    unsigned int v;
-    unsigned int spins = 0;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-      if (++spins > (1u << 28)) { printf("sed: GRU group barrier timed out\n"); __trap(); }
-    } while (v < target);
-  }
-  half_barrier_sync(bar_id);
+__device__ __forceinline__ uint4 ld_relaxed_v4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_v4(uint4* p, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+// fp32 -> {bf16 hi (low half-word), bf16 lo = bf16(v - hi) (high half-word)}: the two terms of the operand split
+__device__ __forceinline__ uint32_t pack_hilo(float v) {
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+  return (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
 }
 
 struct GruPersist {
-  unsigned int* sync_ctr;   // [tiles][2 directions][2 halves] arrive counters (zeroed by the host entry point)
+  uint4* xchg;              // [tiles][2 directions][2 slots][32 rows][values / 2] exchange area (zeroed by the host entry point)
   int B, T, b_base;
 };
 
@@ -225,40 +232,54 @@ __device__ __forceinline__ void stage_split(const float* __restrict__ src, long 
     *reinterpret_cast<uint2*>(s_lo + r * ld + c4 * 4) = make_uint2(l0, l1);
   }
 }
-// The per-step exchange tile (16 rows of the group's h / dGh, read through L2): compile-time shape so that a thread
-// issues its loads in batches of 8 independent 16-byte requests before converting any of them -- one L2 round trip
-// per batch instead of one per element (this staging, not the matrix product, was the per-step critical path).
-template <int kRows, int kCols, int kThreadsN>
-__device__ __forceinline__ void stage_split_tile(const float* __restrict__ src, long long src_stride, bool have,
-                                                 int valid_rows, __nv_bfloat16* __restrict__ s_hi,
-                                                 __nv_bfloat16* __restrict__ s_lo, int ld, int tid) {
-  constexpr int kC4 = kCols / 4;
-  constexpr int kPer = kRows * kC4 / kThreadsN;
-  static_assert(kRows * kC4 % kThreadsN == 0 && kPer % 8 == 0, "tile must split into batches of 8 per thread");
+// The per-step exchange tile: 16 rows of kV4PerRow 16-byte vectors {hi|lo, tag, hi|lo, tag} in an exchange slot (L2).
+// A thread issues its loads in batches of 8 independent requests, checks the 16 tags, and repeats the batch until all
+// match; then the hi / lo halves go to the shared operand tiles.  Rows >= valid_rows (ragged last batch tile) are
+// never produced: they are zero-filled without polling.
+template <int kV4PerRow>
+__device__ __forceinline__ void stage_flagged_tile(const uint4* __restrict__ slot, uint32_t tag, bool have,
+                                                   int valid_rows, __nv_bfloat16* __restrict__ s_hi,
+                                                   __nv_bfloat16* __restrict__ s_lo, int ld, int ht) {
+  constexpr int kPer = 16 * kV4PerRow / 128;          // vectors per thread; vector u of thread ht: index u * 128 + ht
+  constexpr int kPerRow = kV4PerRow / 128;            // ... which lies in row u / kPerRow (ht < 128)
+  constexpr int kBatch = 16;                          // requests in flight per thread (8: 0.03 ms slower per launch)
+  static_assert(kPer % kBatch == 0 && kV4PerRow % 128 == 0, "tile must split into whole batches per thread");
+  const int n_valid = have ? min(kPer, max(valid_rows, 0) * kPerRow) : 0;
+#pragma unroll 1
+  for (int base = 0; base < kPer; base += kBatch) {
+    uint4 v[kBatch];
+    if (base < n_valid) {
+      unsigned int spins = 0;
+      bool ok;
+      do {
+        // all requests of the batch first, THEN the tag checks: a check right behind its load stalls the in-order
+        // issue of the next load on a full L2 round trip (measured: it serialized every load of the step)
 #pragma unroll
-  for (int base = 0; base < kPer; base += 8) {
-    float4 v[8];
+        for (int u = 0; u < kBatch; ++u) v[u] = ld_relaxed_v4(slot + min(base + u, n_valid - 1) * 128 + ht);
+        unsigned int bad = 0u;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int i = (base + u) * kThreadsN + tid;
-      const int r = i / kC4, c4 = i - r * kC4;
-      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (have && r < valid_rows) v[u] = __ldcg(reinterpret_cast<const float4*>(src + r * src_stride + c4 * 4));
+        for (int u = 0; u < kBatch; ++u) bad |= (v[u].y ^ tag) | (v[u].w ^ tag);
+        ok = bad == 0u;
+        if (!ok && ++spins > (1u << 24)) { printf("sed: GRU exchange timed out (tag %u)\n", tag); __trap(); }
+      } while (!ok);
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int i = (base + u) * kThreadsN + tid;
-      const int r = i / kC4, c4 = i - r * kC4;
-      uint32_t h0, l0, h1, l1;
-      split2(v[u].x, v[u].y, h0, l0);
-      split2(v[u].z, v[u].w, h1, l1);
-      *reinterpret_cast<uint2*>(s_hi + r * ld + c4 * 4) = make_uint2(h0, h1);
-      *reinterpret_cast<uint2*>(s_lo + r * ld + c4 * 4) = make_uint2(l0, l1);
+    for (int u = 0; u < kBatch; ++u) {
+      const int i = (base + u) * 128 + ht;
+      const int r = i / kV4PerRow, c4 = i - r * kV4PerRow;
+      uint32_t hi = 0u, lo = 0u;
+      if (base + u < n_valid) {
+        hi = __byte_perm(v[u].x, v[u].z, 0x5410);
+        lo = __byte_perm(v[u].x, v[u].z, 0x7632);
+      }
+      *reinterpret_cast<uint32_t*>(s_hi + r * ld + c4 * 2) = hi;
+      *reinterpret_cast<uint32_t*>(s_lo + r * ld + c4 * 2) = lo;
     }
   }
 }
 constexpr int kLdK = kPH + 8;          // bf16 row stride of the K = 256 tiles (528 B: conflict-free fragment loads)
-constexpr int kLdG = 3 * kPH + 8;      // bf16 row stride of the K = 768 tiles
+constexpr int kLdB = 3 * kPJ + 8;      // bf16 row stride of the K = 96 tiles of the backward (208 B: conflict-free)
+constexpr int kBwdXchgValues = kPGroup * kPH;   // backward exchange, per batch row: 8 producers x 256 partial sums
 
 // Forward.  CTA r of a group owns hidden units [32r, 32r+32) of 32 batch rows: a 32 x 96 x 256 product per step
 // (gate columns ordered r | z | n).  Warp w: batch rows 16*(w&1).., unit octet w>>1, i.e. the three n-tiles
@@ -283,7 +304,7 @@ gru_fwd_persistent_kernel(const float* __restrict__ Gx, const float* __restrict_
                 tid, kPThreads);
   const int mt = warp & 1, oct = warp >> 1;                             // half (16 batch rows) / unit octet
   const int ht = oct * 32 + lane;                                       // thread index within the half (0..127)
-  unsigned int* ctr = q.sync_ctr + ((blockIdx.y * 2 + d) * 2 + mt);
+  uint4* xbase = q.xchg + (long long)(blockIdx.y * 2 + d) * 2 * kPB * (kPH / 2);   // this group's two slots
   __syncthreads();                                                      // the W_hh slice is staged
   const int row0 = mt * 16 + gid;                                       // this thread's rows: row0, row0 + 8
   const int jl = oct * 8 + tig * 2;                                     // its units: j0 + jl, j0 + jl + 1
@@ -295,7 +316,6 @@ gru_fwd_persistent_kernel(const float* __restrict__ Gx, const float* __restrict_
   float hprev[2][2] = {{0.f, 0.f}, {0.f, 0.f}};                         // [row][unit]
   for (int s = 0; s < T; ++s) {
     const int tt = d == 0 ? s : T - 1 - s;
-    const int tp = d == 0 ? tt - 1 : tt + 1;
     // this step's input projections: issued now, consumed after the recurrent product
     float2 gx[2][3];
 #pragma unroll
@@ -309,11 +329,10 @@ gru_fwd_persistent_kernel(const float* __restrict__ Gx, const float* __restrict_
         for (int g = 0; g < 3; ++g) gx[rr][g] = __ldg(reinterpret_cast<const float2*>(gp + g * H));
       }
     }
-    // h_{t-1} of this half's 16 rows, produced by all 8 CTAs of the group, is in L2
-    if (s > 0) group_barrier_half(ctr, (unsigned int)(kPGroup * s), 1 + mt, ht == 0);
-    else half_barrier_sync(1 + mt);
-    stage_split_tile<16, kPH, 128>(out + ((long long)(b0 + mt * 16) * T + tp) * 2 * H + d * H, (long long)T * 2 * H,
-                                   s > 0, B - b0 - mt * 16, sHh + mt * 16 * kLdK, sHl + mt * 16 * kLdK, kLdK, ht);
+    // h_{t-1} of this half's 16 rows, produced by all 8 CTAs of the group: slot (s - 1) & 1, tag s
+    half_barrier_sync(1 + mt);                                          // last step's reads of the operand tile are done
+    stage_flagged_tile<kPH / 2>(xbase + ((s + 1) & 1) * kPB * (kPH / 2) + mt * 16 * (kPH / 2), (uint32_t)s, s > 0,
+                                B - b0 - mt * 16, sHh + mt * 16 * kLdK, sHl + mt * 16 * kLdK, kLdK, ht);
     half_barrier_sync(1 + mt);
     float acc[3][4];
 #pragma unroll
@@ -365,6 +384,9 @@ gru_fwd_persistent_kernel(const float* __restrict__ Gx, const float* __restrict_
           rv[u] = r; zv[u] = z; nv[u] = n; gv[u] = ghn;
           hprev[rr][u] = hn[u];
         }
+        // first the exchange word the other 7 CTAs (and this one) are polling for, then the tensors of record
+        st_relaxed_v4(xbase + (s & 1) * kPB * (kPH / 2) + (row0 + rr * 8) * (kPH / 2) + (j >> 1), pack_hilo(hn[0]),
+                       (uint32_t)(s + 1), pack_hilo(hn[1]), (uint32_t)(s + 1));
         *reinterpret_cast<float2*>(out + ((long long)b * T + tt) * 2 * H + d * H + j) = make_float2(hn[0], hn[1]);
         float* gs = gates + (((long long)b * T + tt) * 2 + d) * 4 * H + j;
         *reinterpret_cast<float2*>(gs) = make_float2(rv[0], rv[1]);
@@ -373,69 +395,125 @@ gru_fwd_persistent_kernel(const float* __restrict__ Gx, const float* __restrict_
         *reinterpret_cast<float2*>(gs + 3 * H) = make_float2(gv[0], gv[1]);
       }
     }
-    // (the next iteration's barrier orders these stores before any other CTA's read, and its leading
-    //  half-barrier orders this step's shared-memory reads before the refill)
+    // (the next iteration's leading half-barrier orders this step's shared-memory reads before the refill)
   }
 }
 
-// BPTT in one cooperative launch, same grouping.  CTA r owns hidden units / W_hh columns [32r, 32r+32): it
-// turns dh of its own units into the gate gradients (which it stores to dGx / dGh -- needed by the
-// weight-gradient GEMMs anyway), meets the group, reads the group's full dGh rows back from L2, and computes
-// its own 32 columns of dh_prev = dGh . W_hh + dh * z (a 32 x 32 x 768 product on the warp-level MMA path), which
-// never leave its registers: the thread that owns accumulator element (row, unit) is the one that consumes it.
+// BPTT in one cooperative launch, same grouping: CTA r owns hidden units [32r, 32r+32) of 32 batch rows.
+//   dh_prev[b, k] = sum over (gate g, unit j) of dGh[b, g, j] * W_hh[g H + j, k]  +  dh[b, k] * z[b, k]
+// Round 1 gave CTA r the 32 COLUMNS k of that product, so it needed the group's full dGh rows every step: 16 rows x
+// 768 values per half, 96 KB as flagged words.  Here CTA r contracts over ITS OWN 96 (gate, unit) rows -- the gate
+// gradients it has just computed, straight from shared memory -- against W_hh[rows of its units, all 256 columns] and
+// gets a PARTIAL sum for every column; the exchange carries the partial sums to the CTA that owns the column
+// (16 rows x 32 columns x 8 producers per half = 32 KB, one batch of 16 requests per thread), which adds the eight
+// partials in producer order (deterministic) and the dh * z term of its own units.  The product of a step no longer
+// waits for the exchange, only the (cheap) gate math of the next step does.
+// Exchange slot layout: [slot][half][consumer CTA][producer CTA][16 rows][16 column pairs] x {p0, tag, p1, tag}, tag =
+// step + 1; slot reuse is safe for the reason given at the top of this section.
 __global__ void __launch_bounds__(kPThreads, 1)
 gru_bwd_persistent_kernel(const float* __restrict__ dout, const float* __restrict__ out, const float* __restrict__ gates,
                           const float* __restrict__ Whh, float* __restrict__ dGx, float* dGh,
                           float* __restrict__ Hprev, __nv_bfloat16* __restrict__ dGx16, __nv_bfloat16* __restrict__ dGh16,
                           __nv_bfloat16* __restrict__ Hprev16, GruPersist q) {
   extern __shared__ __align__(16) uint8_t smem_gru[];
-  __nv_bfloat16* sDh = reinterpret_cast<__nv_bfloat16*>(smem_gru);      // [32][kLdG]  dGh rows of the group, hi
-  __nv_bfloat16* sDl = sDh + kPB * kLdG;                                //             lo
-  __nv_bfloat16* sWh = sDl + kPB * kLdG;                                // [32][kLdG]  W_hh[:, k0:k0+32]^T, hi
-  __nv_bfloat16* sWl = sWh + kPJ * kLdG;                                //             lo
+  __nv_bfloat16* sWh = reinterpret_cast<__nv_bfloat16*>(smem_gru);      // [256][kLdB]  W_hh[g H + u0 + jl][n] at [n][g 32 + jl], hi
+  __nv_bfloat16* sWl = sWh + kPH * kLdB;                                //              lo
+  __nv_bfloat16* sAh = sWl + kPH * kLdB;                                // [32][kLdB]   this step's dGh of the own units, hi
+  __nv_bfloat16* sAl = sAh + kPB * kLdB;                                //              lo
   constexpr int H = kPH;
   const int B = q.B, T = q.T;
-  const int k0 = blockIdx.x * kPJ, b0 = q.b_base + blockIdx.y * kPB, d = blockIdx.z;
+  const int r_cta = blockIdx.x, u0 = r_cta * kPJ, b0 = q.b_base + blockIdx.y * kPB, d = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int gid = lane >> 2, tig = lane & 3;
   const float* W = Whh + (long long)d * 3 * H * H;
-  for (int i = tid; i < 3 * H * kPJ; i += kPThreads) {                  // transposed slice: sW[kl][row] = W[row][k0 + kl]
-    const int row = i / kPJ, kl = i - row * kPJ;
-    const float v = W[(long long)row * H + k0 + kl];
-    const float hi = __bfloat162float(__float2bfloat16_rn(v));
-    sWh[kl * kLdG + row] = __float2bfloat16_rn(hi);
-    sWl[kl * kLdG + row] = __float2bfloat16_rn(v - hi);
+  for (int i = tid; i < 3 * kPJ * (H / 4); i += kPThreads) {            // coalesced rows of W_hh, transposed into sW
+    const int row = i / (H / 4), n4 = i - row * (H / 4);                // row = g * 32 + jl
+    const int g = row / kPJ, jl = row - g * kPJ;
+    const float4 v = *reinterpret_cast<const float4*>(W + ((long long)g * H + u0 + jl) * H + n4 * 4);
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __nv_bfloat16 hi = __float2bfloat16_rn(vv[e]);
+      sWh[(n4 * 4 + e) * kLdB + row] = hi;
+      sWl[(n4 * 4 + e) * kLdB + row] = __float2bfloat16_rn(vv[e] - __bfloat162float(hi));
+    }
   }
   const int mt = warp & 1, oct = warp >> 1;
-  const int ht = oct * 32 + lane;                                       // thread index within the 16-row half
-  unsigned int* ctr = q.sync_ctr + ((blockIdx.y * 2 + d) * 2 + mt);
-  __syncthreads();                                                      // the transposed W_hh slice is staged
+  // exchange area of this group: [2 slots][2 halves][8 consumers][8 producers][16 rows][16 pairs]
+  constexpr int kPairVecs = 16 * 16;                                    // vectors of one (consumer, producer) block
+  uint4* xbase = q.xchg + (long long)(blockIdx.y * 2 + d) * 2 * 2 * kPGroup * kPGroup * kPairVecs;
+  __syncthreads();                                                      // the W_hh slice is staged
   const int row0 = mt * 16 + gid;
-  const int j = k0 + oct * 8 + tig * 2;                                 // this thread's units: j, j + 1
-  float carry[2][2] = {{0.f, 0.f}, {0.f, 0.f}};                         // dh flowing back from the later time step
+  const int jl = oct * 8 + tig * 2;                                     // this thread's units: u0 + jl, u0 + jl + 1
+  const int j = u0 + jl;
+  float dhz[2][2] = {{0.f, 0.f}, {0.f, 0.f}};                           // dh * z of the previous step (own units)
   for (int bs = 0; bs < T; ++bs) {
     const int tt = d == 0 ? T - 1 - bs : bs;
     const int tp = d == 0 ? tt - 1 : tt + 1;
     const bool has_prev = tp >= 0 && tp < T;
-    float dhz[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    // ---- this step's saved activations: requested before the exchange is polled
+    float2 r2[2], z2[2], n2[2], g2[2], hp2[2], do2[2];
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
       const int b = b0 + row0 + rr * 8;
+      r2[rr] = z2[rr] = n2[rr] = g2[rr] = hp2[rr] = do2[rr] = make_float2(0.f, 0.f);
       if (b < B) {
         const long long bt = (long long)b * T + tt;
         const float* gs = gates + (bt * 2 + d) * 4 * H + j;
-        const float2 r2 = __ldg(reinterpret_cast<const float2*>(gs)), z2 = __ldg(reinterpret_cast<const float2*>(gs + H));
-        const float2 n2 = __ldg(reinterpret_cast<const float2*>(gs + 2 * H)),
-                     g2 = __ldg(reinterpret_cast<const float2*>(gs + 3 * H));
-        float2 hp2 = make_float2(0.f, 0.f);
-        if (has_prev) hp2 = __ldg(reinterpret_cast<const float2*>(out + ((long long)b * T + tp) * 2 * H + d * H + j));
-        const float2 do2 = __ldg(reinterpret_cast<const float2*>(dout + bt * 2 * H + d * H + j));
-        float drp[2], dzp[2], dnp[2], dnr[2];
+        r2[rr] = __ldg(reinterpret_cast<const float2*>(gs));
+        z2[rr] = __ldg(reinterpret_cast<const float2*>(gs + H));
+        n2[rr] = __ldg(reinterpret_cast<const float2*>(gs + 2 * H));
+        g2[rr] = __ldg(reinterpret_cast<const float2*>(gs + 3 * H));
+        if (has_prev) hp2[rr] = __ldg(reinterpret_cast<const float2*>(out + ((long long)b * T + tp) * 2 * H + d * H + j));
+        do2[rr] = __ldg(reinterpret_cast<const float2*>(dout + bt * 2 * H + d * H + j));
+      }
+    }
+    // ---- dh flowing back from the later time step: eight partial sums per (row, unit) + dh * z
+    float carry[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    if (bs > 0) {
+      const uint4* xs = xbase + ((((bs - 1) & 1) * 2 + mt) * kPGroup + r_cta) * kPGroup * kPairVecs + gid * 16 + (jl >> 1);
+      const uint32_t tag = (uint32_t)bs;
+      const bool need[2] = {b0 + row0 < B, b0 + row0 + 8 < B};
+      uint4 v[16];                                                      // [producer][rr]
+      unsigned int spins = 0;
+      bool ok;
+      do {
+#pragma unroll
+        for (int rp = 0; rp < kPGroup; ++rp)
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr)
+            v[rp * 2 + rr] = ld_relaxed_v4(xs + rp * kPairVecs + (need[rr] ? rr * 8 * 16 : 0));
+        unsigned int bad = 0u;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) bad |= (v[u].y ^ tag) | (v[u].w ^ tag);
+        ok = bad == 0u || !need[0];                                     // (rows come in order: !need[0] => no row of this thread)
+        if (!ok && ++spins > (1u << 24)) { printf("sed: GRU exchange timed out (tag %u)\n", tag); __trap(); }
+      } while (!ok);
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        float sx = 0.f, sy = 0.f;
+#pragma unroll
+        for (int rp = 0; rp < kPGroup; ++rp) {
+          sx += __uint_as_float(v[rp * 2 + rr].x);
+          sy += __uint_as_float(v[rp * 2 + rr].z);
+        }
+        carry[rr][0] = need[rr] ? sx + dhz[rr][0] : 0.f;
+        carry[rr][1] = need[rr] ? sy + dhz[rr][1] : 0.f;
+      }
+    }
+    half_barrier_sync(1 + mt);                                          // last step's reads of the A tile are done
+    // ---- gate gradients of the own (row, unit) pairs
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int b = b0 + row0 + rr * 8;
+      float drp[2] = {0.f, 0.f}, dzp[2] = {0.f, 0.f}, dnp[2] = {0.f, 0.f}, dnr[2] = {0.f, 0.f};
+      if (b < B) {
+        const long long bt = (long long)b * T + tt;
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-          const float r = u ? r2.y : r2.x, z = u ? z2.y : z2.x, n = u ? n2.y : n2.x, ghn = u ? g2.y : g2.x;
-          const float hp = u ? hp2.y : hp2.x;
-          const float dh = (u ? do2.y : do2.x) + carry[rr][u];
+          const float r = u ? r2[rr].y : r2[rr].x, z = u ? z2[rr].y : z2[rr].x, n = u ? n2[rr].y : n2[rr].x;
+          const float ghn = u ? g2[rr].y : g2[rr].x, hp = u ? hp2[rr].y : hp2[rr].x;
+          const float dh = (u ? do2[rr].y : do2[rr].x) + carry[rr][u];
           dnp[u] = dh * (1.f - z) * (1.f - n * n);
           dzp[u] = dh * (hp - n) * z * (1.f - z);
           drp[u] = dnp[u] * ghn * r * (1.f - r);
@@ -450,7 +528,7 @@ gru_bwd_persistent_kernel(const float* __restrict__ dout, const float* __restric
         *reinterpret_cast<float2*>(gh) = make_float2(drp[0], drp[1]);
         *reinterpret_cast<float2*>(gh + H) = make_float2(dzp[0], dzp[1]);
         *reinterpret_cast<float2*>(gh + 2 * H) = make_float2(dnr[0], dnr[1]);
-        *reinterpret_cast<float2*>(Hprev + (bt * 2 + d) * H + j) = hp2;
+        *reinterpret_cast<float2*>(Hprev + (bt * 2 + d) * H + j) = hp2[rr];
         if (dGx16) {      // bf16 copies for the weight-gradient GEMMs that follow (dW_ih = dGx^T X, dW_hh = dGh^T Hprev)
           __nv_bfloat16* gx16 = dGx16 + (bt * 2 + d) * 3 * H + j;
           __nv_bfloat16* gh16 = dGh16 + (bt * 2 + d) * 3 * H + j;
@@ -461,64 +539,95 @@ gru_bwd_persistent_kernel(const float* __restrict__ dout, const float* __restric
           *reinterpret_cast<uint32_t*>(gh16) = pr;
           *reinterpret_cast<uint32_t*>(gh16 + H) = pz;
           *reinterpret_cast<uint32_t*>(gh16 + 2 * H) = pack_bf16x2(dnr[0], dnr[1]);
-          *reinterpret_cast<uint32_t*>(Hprev16 + (bt * 2 + d) * H + j) = pack_bf16x2(hp2.x, hp2.y);
+          *reinterpret_cast<uint32_t*>(Hprev16 + (bt * 2 + d) * H + j) = pack_bf16x2(hp2[rr].x, hp2[rr].y);
         }
       }
+      // the A operand of this step's product: dGh of (row, gate, own unit), zero for rows beyond the batch
+      const int ar = (row0 + rr * 8) * kLdB + jl;
+      uint32_t hi, lo;
+      split2(drp[0], drp[1], hi, lo);
+      *reinterpret_cast<uint32_t*>(sAh + ar) = hi;
+      *reinterpret_cast<uint32_t*>(sAl + ar) = lo;
+      split2(dzp[0], dzp[1], hi, lo);
+      *reinterpret_cast<uint32_t*>(sAh + ar + kPJ) = hi;
+      *reinterpret_cast<uint32_t*>(sAl + ar + kPJ) = lo;
+      split2(dnr[0], dnr[1], hi, lo);
+      *reinterpret_cast<uint32_t*>(sAh + ar + 2 * kPJ) = hi;
+      *reinterpret_cast<uint32_t*>(sAl + ar + 2 * kPJ) = lo;
     }
-    if (bs == T - 1) break;                              // dh of the step before the first is not needed
-    // every CTA's dGh slice of this step (this half's 16 rows) is in L2
-    group_barrier_half(ctr, (unsigned int)(kPGroup * (bs + 1)), 1 + mt, ht == 0);
-    stage_split_tile<16, 3 * kPH, 128>(dGh + (((long long)(b0 + mt * 16) * T + tt) * 2 + d) * 3 * H,
-                                       (long long)T * 2 * 3 * H, true, B - b0 - mt * 16, sDh + mt * 16 * kLdG,
-                                       sDl + mt * 16 * kLdG, kLdG, ht);
-    half_barrier_sync(1 + mt);
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const __nv_bfloat16* ah = sDh + row0 * kLdG + tig * 2;
-    const __nv_bfloat16* al = sDl + row0 * kLdG + tig * 2;
-    const __nv_bfloat16* wh = sWh + (oct * 8 + gid) * kLdG + tig * 2;
-    const __nv_bfloat16* wl = sWl + (oct * 8 + gid) * kLdG + tig * 2;
-#pragma unroll 4
-    for (int kk = 0; kk < 3 * H; kk += 16) {
-      uint32_t a_hi[4], a_lo[4], b_hi[2], b_lo[2];
+    if (bs == T - 1) break;                                             // dh of the step before the first is not needed
+    half_barrier_sync(1 + mt);                                          // the half's A tile is complete
+    // ---- partial[16 rows][64 columns oct * 64 ..] = A (16 x 96) . W_hh[own rows][columns]
+    float acc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+    const __nv_bfloat16* ah = sAh + row0 * kLdB + tig * 2;
+    const __nv_bfloat16* al = sAl + row0 * kLdB + tig * 2;
+    const __nv_bfloat16* wh = sWh + (oct * 64 + gid) * kLdB + tig * 2;
+    const __nv_bfloat16* wl = sWl + (oct * 64 + gid) * kLdB + tig * 2;
+#pragma unroll
+    for (int kk = 0; kk < 3 * kPJ; kk += 16) {
+      uint32_t a_hi[4], a_lo[4];
       a_hi[0] = *reinterpret_cast<const uint32_t*>(ah + kk);
-      a_hi[1] = *reinterpret_cast<const uint32_t*>(ah + 8 * kLdG + kk);
+      a_hi[1] = *reinterpret_cast<const uint32_t*>(ah + 8 * kLdB + kk);
       a_hi[2] = *reinterpret_cast<const uint32_t*>(ah + kk + 8);
-      a_hi[3] = *reinterpret_cast<const uint32_t*>(ah + 8 * kLdG + kk + 8);
+      a_hi[3] = *reinterpret_cast<const uint32_t*>(ah + 8 * kLdB + kk + 8);
       a_lo[0] = *reinterpret_cast<const uint32_t*>(al + kk);
-      a_lo[1] = *reinterpret_cast<const uint32_t*>(al + 8 * kLdG + kk);
+      a_lo[1] = *reinterpret_cast<const uint32_t*>(al + 8 * kLdB + kk);
       a_lo[2] = *reinterpret_cast<const uint32_t*>(al + kk + 8);
-      a_lo[3] = *reinterpret_cast<const uint32_t*>(al + 8 * kLdG + kk + 8);
-      b_hi[0] = *reinterpret_cast<const uint32_t*>(wh + kk);
-      b_hi[1] = *reinterpret_cast<const uint32_t*>(wh + kk + 8);
-      b_lo[0] = *reinterpret_cast<const uint32_t*>(wl + kk);
-      b_lo[1] = *reinterpret_cast<const uint32_t*>(wl + kk + 8);
-      mma_bf16_m16n8k16(acc, a_hi, b_hi);
-      mma_bf16_m16n8k16(acc, a_lo, b_hi);
-      mma_bf16_m16n8k16(acc, a_hi, b_lo);
+      a_lo[3] = *reinterpret_cast<const uint32_t*>(al + 8 * kLdB + kk + 8);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        uint32_t b_hi[2], b_lo[2];
+        b_hi[0] = *reinterpret_cast<const uint32_t*>(wh + nt * 8 * kLdB + kk);
+        b_hi[1] = *reinterpret_cast<const uint32_t*>(wh + nt * 8 * kLdB + kk + 8);
+        b_lo[0] = *reinterpret_cast<const uint32_t*>(wl + nt * 8 * kLdB + kk);
+        b_lo[1] = *reinterpret_cast<const uint32_t*>(wl + nt * 8 * kLdB + kk + 8);
+        mma_bf16_m16n8k16(acc[nt], a_hi, b_hi);
+        mma_bf16_m16n8k16(acc[nt], a_lo, b_hi);
+        mma_bf16_m16n8k16(acc[nt], a_hi, b_lo);
+      }
     }
+    // ---- the partial sums travel to the CTAs that own their columns (accumulator element i: row gid + 8 (i >> 1),
+    //      column oct * 64 + nt * 8 + tig * 2 + (i & 1))
+    {
+      const uint32_t tg = (uint32_t)(bs + 1);
+      uint4* xs = xbase + ((bs & 1) * 2 + mt) * kPGroup * kPGroup * kPairVecs + r_cta * kPairVecs + gid * 16 + tig;
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr)
+      for (int nt = 0; nt < 8; ++nt) {
+        const int col = oct * 64 + nt * 8;                              // first column of the n tile
+        uint4* xc = xs + (col >> 5) * kPGroup * kPairVecs + ((col & 31) >> 1);
 #pragma unroll
-      for (int u = 0; u < 2; ++u) carry[rr][u] = acc[rr * 2 + u] + dhz[rr][u];
-    // (the next barrier's leading half-barrier orders these shared-memory reads before the refill)
+        for (int rr = 0; rr < 2; ++rr)
+          if (b0 + row0 + rr * 8 < B)
+            st_relaxed_v4(xc + rr * 8 * 16, __float_as_uint(acc[nt][rr * 2]), tg, __float_as_uint(acc[nt][rr * 2 + 1]), tg);
+      }
+    }
   }
 }
 
 // Cooperative launches (co-residency of a group is what makes the barrier deadlock-free) over chunks of
 // batch tiles that fit the device at one CTA per SM.
+// exchange area of one batch tile: 2 directions x 2 slots x 32 rows x (values per row) 8-byte words
+constexpr size_t gru_xchg_tile_bytes(int values_per_row) { return (size_t)2 * 2 * kPB * values_per_row * 8; }
+
 template <typename F>
-int launch_gru_persistent(const void* kern, const char* name, size_t smem, int B, int T, unsigned int* sync_ws,
-                          cudaStream_t stream, F fill_args) {
+int launch_gru_persistent(const void* kern, const char* name, size_t smem, int B, int T, void* xchg_ws,
+                          int values_per_row, cudaStream_t stream, F fill_args) {
   SED_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   SED_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPThreads, smem));
   const int max_tiles = per_sm * sm_count() / (kPGroup * 2);
   SED_REQUIRE(max_tiles >= 1, "%s: the device cannot hold one batch tile", name);
   const int tiles = (B + kPB - 1) / kPB;
-  SED_CUDA(cudaMemsetAsync(sync_ws, 0, sizeof(unsigned int) * 4 * (size_t)tiles, stream));
+  const size_t tile_bytes = gru_xchg_tile_bytes(values_per_row);
+  SED_REQUIRE((reinterpret_cast<uintptr_t>(xchg_ws) & 15) == 0, "%s: the workspace must be 16-byte aligned", name);
+  SED_CUDA(cudaMemsetAsync(xchg_ws, 0, tile_bytes * (size_t)tiles, stream));      // tag 0 = nothing produced yet
   for (int t0 = 0; t0 < tiles; t0 += max_tiles) {
     const int nt = tiles - t0 < max_tiles ? tiles - t0 : max_tiles;
-    GruPersist q{sync_ws + 4 * t0, B, T, t0 * kPB};
+    GruPersist q{reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(xchg_ws) + tile_bytes * (size_t)t0), B, T, t0 * kPB};
     void* args[12];
     const int n = fill_args(args);
     args[n] = &q;
@@ -580,6 +689,14 @@ using namespace sed;
 
 extern "C" {
 
+long long sed_gru_workspace_bytes(int B, int H, int backward) {
+  const long long tiles = (B + kPB - 1) / kPB;
+  const long long step_kernels = backward ? 4LL * B * H * (long long)sizeof(float) : 16;   // (2,2,B,H) carry / nothing
+  if (H != kPH) return step_kernels;
+  const long long persistent = tiles * (long long)gru_xchg_tile_bytes(backward ? kBwdXchgValues : kPH);
+  return persistent > step_kernels ? persistent : step_kernels;
+}
+
 int sed_gru_fwd(const float* gx, const float* w_hh, const float* b_hh, float* out, float* gates, void* sync_ws,
                 int B, int T, int H, sed_stream_t stream) {
   SED_REQUIRE(gx && w_hh && b_hh && out && gates, "sed_gru_fwd: null pointer");
@@ -587,8 +704,8 @@ int sed_gru_fwd(const float* gx, const float* w_hh, const float* b_hh, float* ou
   if (B == 0 || T == 0) return 0;
   if (H == kPH && sync_ws != nullptr) {
     const size_t psmem = sizeof(__nv_bfloat16) * (size_t)(2 * 3 * kPJ * kLdK + 2 * kPB * kLdK);
-    return launch_gru_persistent((const void*)gru_fwd_persistent_kernel, "sed_gru_fwd", psmem, B, T,
-                                 reinterpret_cast<unsigned int*>(sync_ws), (cudaStream_t)stream, [&](void** a) {
+    return launch_gru_persistent((const void*)gru_fwd_persistent_kernel, "sed_gru_fwd", psmem, B, T, sync_ws, kPH,
+                                 (cudaStream_t)stream, [&](void** a) {
                                    a[0] = (void*)&gx; a[1] = (void*)&w_hh; a[2] = (void*)&b_hh; a[3] = (void*)&out; a[4] = (void*)&gates;
                                    return 5;
                                  });
@@ -613,10 +730,10 @@ int sed_gru_bwd(const float* dout, const float* out, const float* gates, const f
   SED_REQUIRE(H % kHT == 0 && H % 4 == 0 && H <= 256, "sed_gru_bwd: hidden size %d unsupported", H);
   if (B == 0 || T == 0) return 0;
   if (H == kPH) {
-    // the carry scratch is not needed (dh never leaves registers); its head holds the group counters
-    const size_t psmem = sizeof(__nv_bfloat16) * (size_t)(2 * kPB * kLdG + 2 * kPJ * kLdG);
-    return launch_gru_persistent((const void*)gru_bwd_persistent_kernel, "sed_gru_bwd", psmem, B, T,
-                                 reinterpret_cast<unsigned int*>(carry), (cudaStream_t)stream, [&](void** a) {
+    // dh never leaves registers; the scratch is the exchange area of the partial sums
+    const size_t psmem = sizeof(__nv_bfloat16) * (size_t)(2 * kPH * kLdB + 2 * kPB * kLdB);
+    return launch_gru_persistent((const void*)gru_bwd_persistent_kernel, "sed_gru_bwd", psmem, B, T, carry, kBwdXchgValues,
+                                 (cudaStream_t)stream, [&](void** a) {
                                    a[0] = (void*)&dout; a[1] = (void*)&out; a[2] = (void*)&gates; a[3] = (void*)&w_hh;
                                    a[4] = (void*)&dgx; a[5] = (void*)&dgh; a[6] = (void*)&hprev;
                                    a[7] = (void*)&dgx_bf16; a[8] = (void*)&dgh_bf16; a[9] = (void*)&hprev_bf16;

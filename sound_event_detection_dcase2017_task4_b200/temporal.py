@@ -36,7 +36,7 @@ def gru_forward(gru, feat, keep):
     gx = gemm.gemm_nt(x3, gemm.split3(w_ih, 1), b_ih)            # (B*T, 2*3H) fp32, fp32-class accuracy
     out = torch.empty((b, t, 2 * h), dtype=F32, device=feat.device)
     gates = torch.empty((b, t, 2, 4, h), dtype=F32, device=feat.device)
-    sync_ws = torch.empty(4 * ((b + 31) // 32) + 4, dtype=torch.int32, device=feat.device)
+    sync_ws = torch.empty(_lib.lib().sed_gru_workspace_bytes(b, h, 0), dtype=torch.uint8, device=feat.device)
     with torch.cuda.device(feat.device):
         call('sed_gru_fwd', gx.data_ptr(), w_hh.data_ptr(), b_hh.data_ptr(), out.data_ptr(), gates.data_ptr(),
              sync_ws.data_ptr(), b, t, h, stream_of(feat))
@@ -52,7 +52,7 @@ def gru_backward(gru, ctx, dout, grad_of):
     dev = dout.device
     w_ih, _, w_hh, _ = _gru_cat(gru)
     dout = dout.contiguous()
-    carry = torch.empty((2, 2, b, h), dtype=F32, device=dev)
+    carry = torch.empty(_lib.lib().sed_gru_workspace_bytes(b, h, 1), dtype=torch.uint8, device=dev)
     dgx = torch.empty((b * t, 2 * 3 * h), dtype=F32, device=dev)
     dgh = torch.empty((b * t, 2 * 3 * h), dtype=F32, device=dev)
     hprev = torch.empty((b * t, 2 * h), dtype=F32, device=dev)
