@@ -186,6 +186,10 @@ int sed_conv_c1_dgrad(const void* dy, const float* w, float* dx, int B, int H, i
 int sed_linear_partials(void);
 int sed_linear_small_fwd(const float* x, const float* W, const float* bias, long long R, int C, int K, float* out,
                          sed_stream_t stream);
+/* Two such maps of the SAME input in one pass over x (AttBlock's att and cla, models.py:137 / :141): out1 (R, K1),
+ * out2 (R, K2); K1 + K2 <= 40, C <= 512. */
+int sed_linear_pair_fwd(const float* x, const float* W1, const float* bias1, int K1, const float* W2, const float* bias2,
+                        int K2, long long R, int C, float* out1, float* out2, sed_stream_t stream);
 int sed_linear_small_bwd(const float* dout, const float* x, const float* W, long long R, int C, int K, float* dx,
                          int dx_accumulate, float* partial_w, float* partial_b, sed_stream_t stream);
 int sed_head_pool_fwd(const float* logit, int B, int T, int K, int ratio, int mode, float* prob, float* clip,

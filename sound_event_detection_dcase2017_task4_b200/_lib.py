@@ -58,6 +58,7 @@ SIGNATURES = {
     'sed_conv_c1_wgrad': [P, P, P, I, I, I, I, P],
     'sed_conv_c1_dgrad': [P, P, P, I, I, I, I, P],
     'sed_linear_partials': [],
+    'sed_linear_pair_fwd': [P, P, P, I, P, P, I, L, I, P, P, P],
     'sed_linear_small_fwd': [P, P, P, L, I, I, P, P],
     'sed_linear_small_bwd': [P, P, P, L, I, I, P, I, P, P, P],
     'sed_head_pool_fwd': [P, I, I, I, I, I, P, P, P, P, P],

@@ -14,6 +14,7 @@ namespace sed {
 namespace {
 
 constexpr int kMaxK = 32;
+constexpr int kMaxPairK = 40;             // K1 + K2 of the paired forward (10 float4 accumulators per thread; 11 spill)
 
 constexpr int kMaxKG = kMaxK / 4;         // K padded to float4 groups
 constexpr int kFwdRows = 64;              // rows per block of the forward kernel
@@ -30,9 +31,9 @@ linear_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W
   const int KG = (K + 3) >> 2, Kp = KG * 4;
   float* s_w = reinterpret_cast<float*>(s_lin4);                 // [C][Kp]
   float* s_x = s_w + (size_t)C * Kp;                             // [64][33]
-  for (int i = threadIdx.x; i < C * Kp; i += blockDim.x) {
-    const int c = i / Kp, k = i % Kp;
-    s_w[i] = k < K ? W[(long long)k * C + c] : 0.f;
+  for (int i = threadIdx.x; i < C * Kp; i += blockDim.x) {       // coalesced rows of W, transposed into shared memory
+    const int k = i / C, c = i - k * C;                          // (reading down a column of W costs one sector per value)
+    s_w[c * Kp + k] = k < K ? W[(long long)k * C + c] : 0.f;
   }
   const int r_loc = threadIdx.x & 63, kh = threadIdx.x >> 6;     // kh is warp-uniform
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -77,6 +78,80 @@ linear_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W
         for (int e = 0; e < 4; ++e) {
           const int k = g * 4 + e;
           if (k < K) out[r * K + k] = v[e] + (bias ? bias[k] : 0.f);
+        }
+      }
+    }
+  }
+}
+
+// Two small linear maps of the SAME input in one pass (AttBlock's att and cla 1x1 convolutions, models.py:137 / :141):
+//   out1[r][k] = b1[k] + sum_c x[r][c] W1[k][c],   out2[r][k] = b2[k] + sum_c x[r][c] W2[k][c].
+// One warp owns 32 rows, one row per lane.  The weights of both maps sit in shared memory as [c][Kp] (Kp = K1 + K2 padded
+// to float4 groups): a thread reads them as warp-broadcast float4s.  x is read ONCE, coalesced (32 lanes = 32 columns
+// of one row), parked in a per-warp [32][33] tile and re-read row-per-lane; the next 32-column chunk is already in
+// registers while the current one is consumed, and nothing but __syncwarp() orders a warp.  (linear_small_fwd_kernel
+// above staged 64 rows per block behind two __syncthreads per chunk and ran once per map: 2 x 100 us for 65 MB.)
+template <int kKG>
+__global__ void __launch_bounds__(128)
+linear_pair_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W1, const float* __restrict__ b1, int K1,
+                       const float* __restrict__ W2, const float* __restrict__ b2, int K2, long long R, int C,
+                       float* __restrict__ out1, float* __restrict__ out2) {
+  extern __shared__ float4 s_lin4[];
+  constexpr int Kp = kKG * 4;
+  float* s_w = reinterpret_cast<float*>(s_lin4);                 // [C][Kp]: columns 0..K1-1 map 1, K1..K1+K2-1 map 2
+  float* s_x = s_w + (size_t)C * Kp;                             // [4 warps][32][33]
+  for (int i = threadIdx.x; i < C * Kp; i += blockDim.x) {       // coalesced rows of W1 / W2, transposed into shared memory
+    const int k = i / C, c = i - k * C;
+    s_w[c * Kp + k] = k < K1 ? W1[(long long)k * C + c] : (k < K1 + K2 ? W2[(long long)(k - K1) * C + c] : 0.f);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* tile = s_x + warp * 32 * 33;
+  const float4* s_w4 = reinterpret_cast<const float4*>(s_w);
+  const long long n_tasks = (R + 31) / 32;
+  for (long long task = (long long)blockIdx.x * 4 + warp; task < n_tasks; task += (long long)gridDim.x * 4) {
+    const long long r0 = task * 32;
+    float4 acc[kKG];
+#pragma unroll
+    for (int g = 0; g < kKG; ++g) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float xr[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) xr[i] = (r0 + i < R && lane < C) ? __ldg(x + (r0 + i) * C + lane) : 0.f;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) tile[i * 33 + lane] = xr[i];
+      __syncwarp();
+      if (c0 + 32 < C) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          xr[i] = (r0 + i < R && c0 + 32 + lane < C) ? __ldg(x + (r0 + i) * C + c0 + 32 + lane) : 0.f;
+      }
+      const int cn = min(32, C - c0);
+#pragma unroll 4
+      for (int c = 0; c < cn; ++c) {
+        const float xv = tile[lane * 33 + c];
+        const float4* wrow = s_w4 + (size_t)(c0 + c) * kKG;
+#pragma unroll
+        for (int g = 0; g < kKG; ++g) {
+          const float4 w = wrow[g];
+          acc[g].x = fmaf(xv, w.x, acc[g].x);
+          acc[g].y = fmaf(xv, w.y, acc[g].y);
+          acc[g].z = fmaf(xv, w.z, acc[g].z);
+          acc[g].w = fmaf(xv, w.w, acc[g].w);
+        }
+      }
+    }
+    const long long r = r0 + lane;
+    if (r < R) {
+#pragma unroll
+      for (int g = 0; g < kKG; ++g) {
+        const float v[4] = {acc[g].x, acc[g].y, acc[g].z, acc[g].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k = g * 4 + e;
+          if (k < K1) out1[r * K1 + k] = v[e] + (b1 ? b1[k] : 0.f);
+          else if (k < K1 + K2) out2[r * K2 + (k - K1)] = v[e] + (b2 ? b2[k - K1] : 0.f);
         }
       }
     }
@@ -234,11 +309,16 @@ __global__ void head_pool_bwd_kernel(const float* __restrict__ prob, const float
   }
 }
 
-// AttBlock tail.  one block per clip; threads over classes for the time reductions.
+// AttBlock tail.  One block per clip.  exp / sigmoid of the (T, K) logits go to shared memory class-major; one warp
+// per class then reduces over time with lanes striding t (fixed shuffle tree: deterministic).  Round 1 let K = 17
+// threads walk their class's 125 frames twice through global memory: 90 us for 2 x 2125 values per clip.
 __global__ void head_att_fwd_kernel(const float* __restrict__ att_logit, const float* __restrict__ cla_logit, int T,
                                     int K, int ratio, int sigmoid_act, float temperature,
                                     float* __restrict__ norm_att /* (B,K,T) */, float* __restrict__ cla /* (B,K,T) */,
                                     float* __restrict__ clip, float* __restrict__ frame /* (B,T*ratio,K) */) {
+  extern __shared__ float s_att[];
+  float* s_e = s_att;                     // [K][T]  exp(clamped logit / temperature) + 1e-6
+  float* s_c = s_att + K * T;             // [K][T]  classifier activation
   const int b = blockIdx.x;
   const float* al = att_logit + (long long)b * T * K;
   const float* cl = cla_logit + (long long)b * T * K;
@@ -247,27 +327,31 @@ __global__ void head_att_fwd_kernel(const float* __restrict__ att_logit, const f
   for (int i = threadIdx.x; i < T * K; i += blockDim.x) {
     const int k = i % K, t = i / K;
     const float a = fminf(fmaxf(al[i], -10.f), 10.f);
-    na[k * T + t] = expf(a / temperature) + 1e-6f;
-    ca[k * T + t] = sigmoid_act ? sigmoidf_(cl[i]) : cl[i];
+    s_e[k * T + t] = expf(a / temperature) + 1e-6f;
+    s_c[k * T + t] = sigmoid_act ? sigmoidf_(cl[i]) : cl[i];
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int k = warp; k < K; k += nwarps) {
     float s = 0.f;
-    for (int t = 0; t < T; ++t) s += na[k * T + t];
+    for (int t = lane; t < T; t += 32) s += s_e[k * T + t];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     float acc = 0.f;
-    for (int t = 0; t < T; ++t) {
-      const float n = na[k * T + t] / s;
+    for (int t = lane; t < T; t += 32) {
+      const float n = s_e[k * T + t] / s;
+      const float c = s_c[k * T + t];
       na[k * T + t] = n;
-      acc += n * ca[k * T + t];
+      ca[k * T + t] = c;
+      acc += n * c;
     }
-    clip[b * K + k] = acc;
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) clip[b * K + k] = acc;
   }
-  __syncthreads();
   if (frame) {
     float* fr = frame + (long long)b * T * ratio * K;
     for (int i = threadIdx.x; i < T * ratio * K; i += blockDim.x) {
       const int k = i % K, tt = i / K;
-      fr[i] = ca[k * T + tt / ratio];
+      fr[i] = s_c[k * T + tt / ratio];
     }
   }
 }
@@ -342,6 +426,32 @@ int sed_linear_small_fwd(const float* x, const float* W, const float* bias, long
   return 0;
 }
 
+int sed_linear_pair_fwd(const float* x, const float* W1, const float* bias1, int K1, const float* W2, const float* bias2,
+                        int K2, long long R, int C, float* out1, float* out2, sed_stream_t stream) {
+  SED_REQUIRE(x && W1 && W2 && out1 && out2, "sed_linear_pair_fwd: null pointer");
+  SED_REQUIRE(K1 >= 1 && K2 >= 1 && K1 + K2 <= kMaxPairK, "sed_linear_pair_fwd: K1 + K2 = %d must be in [2, %d]", K1 + K2,
+              kMaxPairK);
+  SED_REQUIRE(C >= 1 && C <= 512, "sed_linear_pair_fwd: C=%d must be in [1, 512]", C);
+  if (R == 0) return 0;
+  const int KG = (K1 + K2 + 3) / 4;
+  const size_t smem = sizeof(float) * ((size_t)C * KG * 4 + 4 * 32 * 33);
+  const long long tasks = (R + 31) / 32;
+  const unsigned grid = (unsigned)((tasks + 3) / 4 < (long long)sm_count() * 2 ? (tasks + 3) / 4 : (long long)sm_count() * 2);
+  cudaStream_t st = (cudaStream_t)stream;
+#define SED_PAIR(G)                                                                                                  \
+  case G:                                                                                                            \
+    SED_CUDA(cudaFuncSetAttribute(linear_pair_fwd_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    linear_pair_fwd_kernel<G><<<grid, 128, smem, st>>>(x, W1, bias1, K1, W2, bias2, K2, R, C, out1, out2);           \
+    break;
+  switch (KG) {
+    SED_PAIR(1) SED_PAIR(2) SED_PAIR(3) SED_PAIR(4) SED_PAIR(5) SED_PAIR(6) SED_PAIR(7) SED_PAIR(8) SED_PAIR(9) SED_PAIR(10)
+    default: SED_REQUIRE(false, "sed_linear_pair_fwd: unsupported K");
+  }
+#undef SED_PAIR
+  SED_LAUNCH_CHECK("linear_pair_fwd_kernel");
+  return 0;
+}
+
 int sed_linear_small_bwd(const float* dout, const float* x, const float* W, long long R, int C, int K, float* dx,
                          int dx_accumulate, float* partial_w, float* partial_b, sed_stream_t stream) {
   SED_REQUIRE(dout && x && W, "sed_linear_small_bwd: null pointer");
@@ -393,8 +503,11 @@ int sed_head_att_fwd(const float* att_logit, const float* cla_logit, int B, int 
                      float temperature, float* norm_att, float* cla, float* clip, float* frame, sed_stream_t stream) {
   SED_REQUIRE(att_logit && cla_logit && norm_att && cla && clip, "sed_head_att_fwd: null pointer");
   if (B == 0) return 0;
-  head_att_fwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(att_logit, cla_logit, T, K, ratio, sigmoid_act, temperature,
-                                                           norm_att, cla, clip, frame);
+  const size_t smem = sizeof(float) * 2 * (size_t)T * K;
+  SED_REQUIRE(smem <= 200 * 1024, "sed_head_att_fwd: T * K = %d does not fit in shared memory", T * K);
+  SED_CUDA(cudaFuncSetAttribute(head_att_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  head_att_fwd_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(att_logit, cla_logit, T, K, ratio, sigmoid_act, temperature,
+                                                              norm_att, cla, clip, frame);
   SED_LAUNCH_CHECK("head_att_fwd_kernel");
   return 0;
 }

@@ -225,8 +225,9 @@ def head_forward(model, feat, ratio, want_frame=True, keep=True):
         hc.kind = 'att'
         ab = model.att_block
         k = ab.att.weight.shape[0]
-        att_logit = ops.linear_small_fwd(feat2d, ab.att.weight.view(k, c), ab.att.bias).view(b, tp, k)
-        cla_logit = ops.linear_small_fwd(feat2d, ab.cla.weight.view(k, c), ab.cla.bias).view(b, tp, k)
+        att_logit, cla_logit = ops.linear_pair_fwd(feat2d, ab.att.weight.view(k, c), ab.att.bias,
+                                                   ab.cla.weight.view(k, c), ab.cla.bias)
+        att_logit, cla_logit = att_logit.view(b, tp, k), cla_logit.view(b, tp, k)
         clip, norm_att, cla, frame = ops.head_att_fwd(att_logit, cla_logit, ratio, ab.activation == 'sigmoid',
                                                       ab.temperature, want_frame)
         if keep:

@@ -224,6 +224,20 @@ def linear_small_fwd(x2d, W, bias):
     return out
 
 
+def linear_pair_fwd(x2d, W1, b1, W2, b2):
+    """Two small linear maps of the same input in one pass over x2d: (x W1^T + b1, x W2^T + b2)."""
+    r, c = x2d.shape
+    k1, k2 = W1.shape[0], W2.shape[0]
+    if c > 512 or k1 + k2 > 40:
+        return linear_small_fwd(x2d, W1, b1), linear_small_fwd(x2d, W2, b2)
+    out1 = _empty((r, k1), F32, x2d)
+    out2 = _empty((r, k2), F32, x2d)
+    with _dev(x2d):
+        call('sed_linear_pair_fwd', x2d.data_ptr(), W1.data_ptr(), ptr(b1), k1, W2.data_ptr(), ptr(b2), k2, r, c,
+             out1.data_ptr(), out2.data_ptr(), stream_of(x2d))
+    return out1, out2
+
+
 def linear_small_bwd(dout, x2d, W, dW, dbias, want_dx=True, dx=None):
     """dx given => accumulate into it (dx += dout @ W)."""
     r, c = x2d.shape

@@ -33,6 +33,25 @@ def test_linear_small_fwd_bwd():
     assert torch.allclose(dx2, 2 * x.grad, rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize('R,C,K1,K2', [(24 * 125, 512, 17, 17), (32000, 512, 17, 17), (77, 96, 5, 10), (33, 512, 20, 20),
+                                       (64, 512, 30, 30)])
+def test_linear_pair_fwd(R, C, K1, K2):
+    """AttBlock's att and cla maps in one pass over the features (sed_linear_pair_fwd): equal to the two single maps
+    and to F.linear; ragged row / column tiles; K1 + K2 > 40 takes the two-launch path."""
+    from sound_event_detection_dcase2017_task4_b200 import ops
+    g = _g(11)
+    x = torch.randn(R, C, generator=g).cuda()
+    W1, W2 = (torch.randn(K1, C, generator=g) * 0.05).cuda(), (torch.randn(K2, C, generator=g) * 0.05).cuda()
+    b1, b2 = torch.randn(K1, generator=g).cuda(), torch.randn(K2, generator=g).cuda()
+    o1, o2 = ops.linear_pair_fwd(x, W1, b1, W2, b2)
+    assert torch.allclose(o1, F.linear(x, W1, b1), rtol=1e-5, atol=1e-5)
+    assert torch.allclose(o2, F.linear(x, W2, b2), rtol=1e-5, atol=1e-5)
+    # same ascending-c fp32 FMA chain per output as the single-map kernel
+    assert torch.equal(o1, ops.linear_small_fwd(x, W1, b1)) and torch.equal(o2, ops.linear_small_fwd(x, W2, b2))
+    o1n, _ = ops.linear_pair_fwd(x, W1, None, W2, None)
+    assert torch.allclose(o1n, F.linear(x, W1), rtol=1e-5, atol=1e-5)
+
+
 @pytest.mark.parametrize('mode', [0, 1])
 def test_head_pool_fwd_bwd(mode):
     """FrameAvg (mean) / FrameMax (max) heads incl. the x8 interpolation (exact copies)."""
