@@ -91,6 +91,12 @@ int sed_conv3x3_tc_fwd(const void* x, const void* wpack, void* y, float* stats_p
 int sed_conv3x3_tc2_grid(int B, int H, int W, int Cin, int Cout);
 int sed_conv3x3_tc2_fwd(const void* x, const void* wpack, void* y, float* stats_partial, int B, int H, int W, int Cin,
                         int Cout, sed_stream_t stream);
+/* Cout = 64 variant with the three kw taps stacked in N (one N = 192 instruction per kernel row and K16 step; the kw
+ * shift is applied between accumulator rows in the epilogue): same contract and statistics workspace as
+ * sed_conv3x3_tc2_fwd; sed_conv3x3_tc2kw_supported tells whether a shape is covered (Cout == 64, Cin in {64, 128}). */
+int sed_conv3x3_tc2kw_supported(int W, int Cin, int Cout);
+int sed_conv3x3_tc2kw_fwd(const void* x, const void* wpack, void* y, float* stats_partial, int B, int H, int W, int Cin,
+                          int Cout, sed_stream_t stream);
 /* Data gradient fused with the FIRST pass of the BatchNorm+ReLU(+2x2 avg-pool) backward of the layer below
  * (F.relu_(bn(conv(x))) [+ F.avg_pool2d], pytorch/models.py:102-113): dx (B,H,W,Cout) is that layer's dA; y_below is
  * its raw conv output (B, Hy, W*pool, Cout) with Hy/pool == H (an odd Hy has a floor-mode tail row), scale/shift

@@ -31,6 +31,8 @@ SIGNATURES = {
     'sed_conv3x3_tc_fwd': [P, P, P, P, I, I, I, I, I, P],
     'sed_conv3x3_tc2_grid': [I, I, I, I, I],
     'sed_conv3x3_tc2_fwd': [P, P, P, P, I, I, I, I, I, P],
+    'sed_conv3x3_tc2kw_supported': [I, I, I],
+    'sed_conv3x3_tc2kw_fwd': [P, P, P, P, I, I, I, I, I, P],
     'sed_conv3x3_tc_dgrad_bnr': [P, P, P, I, I, I, I, I, P, I, P, P, I, P, P],
     'sed_conv3x3_tc_wgrad_splits': [I, I, I, I, I],
     'sed_conv3x3_tc_wgrad_use_pairs': [I],

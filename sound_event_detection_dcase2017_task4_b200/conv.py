@@ -25,6 +25,12 @@ def pack_weights(w_oihw, want_fwd=True, want_dgrad=True):
 
 # CTA-pair (tcgen05.mma.cta_group::2) kernel: measured 33.9 vs 35.7 ms/step (tools/ab_step.py conv.USE_2CTA=0,1)
 USE_2CTA = True
+# Cout = 64: the three kw taps stacked in N (csrc/conv_halo2_kw_tc.cu), A/B switch for tools/ab_step.py.  Used from
+# KWSTACK_MIN_CIN input channels on: measured at batch 256 (tools/probe_kwstack.py) 128 -> 64 at W = 32: 0.64 -> 0.44 ms
+# (944 -> 1370 TFLOP/s); 64 -> 64 at W = 64: 1.20 -> 1.40 ms -- with one K block per tile the 12 instructions of a tile take
+# 1150 cycles and the epilogue's 64 shuffles per warp and tile ~1400 (1.21 ms even without the cross-warp mailbox).
+USE_KWSTACK = True
+KWSTACK_MIN_CIN = 128
 
 
 def conv3x3(x, wpack, cout, want_stats=False):
@@ -40,7 +46,10 @@ def conv3x3(x, wpack, cout, want_stats=False):
         if want_stats:
             grid = getattr(_lib.lib(), 'sed_conv3x3_tc2_grid' if pair else 'sed_conv3x3_tc_grid')(b, h, w, cin, cout)
             stats = torch.empty((grid, 2, cout), dtype=torch.float32, device=x.device)
-        _lib.call('sed_conv3x3_tc2_fwd' if pair else 'sed_conv3x3_tc_fwd', x.data_ptr(), wpack.data_ptr(), y.data_ptr(),
+        entry = 'sed_conv3x3_tc2_fwd' if pair else 'sed_conv3x3_tc_fwd'
+        if pair and USE_KWSTACK and cin >= KWSTACK_MIN_CIN and _lib.lib().sed_conv3x3_tc2kw_supported(w, cin, cout):
+            entry = 'sed_conv3x3_tc2kw_fwd'
+        _lib.call(entry, x.data_ptr(), wpack.data_ptr(), y.data_ptr(),
                   _lib.ptr(stats), b, h, w, cin, cout, _lib.stream_of(x))
     return (y, stats) if want_stats else y
 

@@ -96,7 +96,12 @@ def test_conv_dgrad_with_fused_bn_reduce(B, H, W, Cin, Cout, pool):
     st.scale = (0.5 + torch.rand(cin_eff, device='cuda'))
     st.scale[::3] *= -1.0
     st.shift = torch.randn(cin_eff, device='cuda') * 0.3
-    dx_plain = conv.conv3x3(dy, wd, cin_eff)
+    was = conv.USE_KWSTACK
+    try:
+        conv.USE_KWSTACK = False                      # same accumulation order as the fused kernel: bit-equal dX
+        dx_plain = conv.conv3x3(dy, wd, cin_eff)
+    finally:
+        conv.USE_KWSTACK = was
     dx, partial = conv.conv3x3_dgrad_bnr(dy, wd, cin_eff, y, st, pool)
     assert torch.equal(dx, dx_plain)
     g = dx.float()
@@ -123,21 +128,67 @@ def test_conv_cta_pair_kernel(B, H, W, Cin, Cout):
     x = _rand((B, H, W, Cin), 21).cuda().to(torch.bfloat16)
     w = (_rand((Cout, Cin, 3, 3), 22) * (2.0 / (9 * Cin)) ** 0.5).cuda()
     wf, _ = conv.pack_weights(w)
-    was = conv.USE_2CTA
+    was = conv.USE_2CTA, conv.USE_KWSTACK
     try:
+        conv.USE_KWSTACK = False              # (the kw-stacked Cout = 64 kernel sums in another order: its own test below)
         conv.USE_2CTA = False
         y1, s1 = conv.conv3x3(x, wf, Cout, want_stats=True)
         conv.USE_2CTA = True
         y2, s2 = conv.conv3x3(x, wf, Cout, want_stats=True)
         torch.cuda.synchronize()
     finally:
-        conv.USE_2CTA = was
+        conv.USE_2CTA, conv.USE_KWSTACK = was
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), padding=1).permute(0, 2, 3, 1)
     err = (y2.float() - ref).abs().max().item()
     assert err <= BF16_EPS * ref.abs().max().item() + 1e-3, err
     assert torch.equal(y1, y2)
     a, b = s1.double().sum(0), s2.double().sum(0)
     assert ((a - b).abs() / (a.abs() + 1.0)).max().item() <= 1e-5
+
+
+@pytest.mark.parametrize('B,H,W,Cin', [
+    (2, 101, 64, 64),      # block1.conv2 / its data gradient: an image row spans two warps (mailbox exchange), H tail
+    (1, 3, 64, 64),        # a single pair tile, mostly tail rows
+    (3, 50, 32, 128),      # block2.conv1 data gradient: a warp is one image row, two 64-channel K blocks
+    (2, 25, 16, 64),       # two image rows per warp
+    (2, 13, 8, 128),       # four image rows per warp
+    (1, 7, 128, 64),       # one image row spans all four warps
+    (150, 4, 32, 64),      # more pair tiles than CTA pairs: persistent loop + accumulator double buffering
+    (64, 1000, 64, 64),    # the bench layer at a quarter of the batch
+])
+def test_conv_kw_stacked_kernel(B, H, W, Cin):
+    """Cout = 64 kernel with the three kw taps stacked in N (sed_conv3x3_tc2kw_fwd): the kw shift is applied between
+    accumulator rows in the epilogue (shuffles + a shared-memory mailbox across warp boundaries).  Against PyTorch fp32 on
+    the same bf16 operands, against the unstacked CTA-pair kernel (same values up to the order of three fp32 additions,
+    i.e. at most one bf16 ulp on a few outputs) and for its BatchNorm statistics."""
+    from sound_event_detection_dcase2017_task4_b200 import _lib, conv
+    Cout = 64
+    assert _lib.lib().sed_conv3x3_tc2kw_supported(W, Cin, Cout) == 1
+    x = _rand((B, H, W, Cin), 41).cuda().to(torch.bfloat16)
+    w = (_rand((Cout, Cin, 3, 3), 42) * (2.0 / (9 * Cin)) ** 0.5).cuda()
+    wf, _ = conv.pack_weights(w)
+    was = conv.USE_KWSTACK, conv.KWSTACK_MIN_CIN
+    try:
+        conv.USE_KWSTACK, conv.KWSTACK_MIN_CIN = False, 64          # (the product uses it from 128 input channels on)
+        y1, s1 = conv.conv3x3(x, wf, Cout, want_stats=True)
+        conv.USE_KWSTACK = True
+        y2, s2 = conv.conv3x3(x, wf, Cout, want_stats=True)
+        y3, s3 = conv.conv3x3(x, wf, Cout, want_stats=True)
+        torch.cuda.synchronize()
+    finally:
+        conv.USE_KWSTACK, conv.KWSTACK_MIN_CIN = was
+    assert torch.equal(y2, y3) and torch.equal(s2, s3)                   # deterministic
+    d = (y1.float() - y2.float()).abs()
+    assert d.max().item() <= BF16_EPS * 2 * y1.float().abs().max().item()
+    assert (d > 0).float().mean().item() <= 0.02                         # a rounding flip here and there, nothing else
+    if B * H <= 4000:
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), padding=1).permute(0, 2, 3, 1)
+        err = (y2.float() - ref).abs().max().item()
+        assert err <= BF16_EPS * ref.abs().max().item() + 1e-3, err
+    a, b = s1.double().sum(0), s2.double().sum(0)          # sums of fp32 accumulators that differ in their last bits
+    n = B * H * W
+    assert ((a[0] - b[0]).abs() / n).max().item() <= 1e-5
+    assert ((a[1] - b[1]).abs() / a[1]).max().item() <= 1e-4
 
 
 @pytest.mark.parametrize('B,H,W,Cin,Cout', [(2, 25, 16, 128, 256), (2, 25, 16, 256, 256), (2, 12, 8, 256, 512),
