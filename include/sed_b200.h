@@ -257,17 +257,19 @@ int sed_gru_bwd(const float* dout, const float* out, const float* gates, const f
  * accumulators and a hi/lo operand split (fp32-class accuracy); q/k/v/dctx must be 16-byte aligned, ld % 4 == 0.
  * Dropout(p_drop) on the probabilities from Philox4x32-10(seed, offset + element/4), element = (score row) * 128 +
  * key (the caller advances its generator by B*H*T*128 draws); p_drop = 0 in eval.
+ * philox_state: NULL, or two device words {seed, offset base} read by the kernel at run time (then `seed` is ignored and
+ * `offset` is relative to the base): lets a captured CUDA graph be replayed with a fresh generator state per step.
  * bwd: dq/dk/dv use the addressing of q/k/v. */
 int sed_attention_fwd(const float* q, const float* k, const float* v, int ldq, int ldk, int ldv, int B, int T, int H,
                       int d, float temperature, float p_drop, unsigned long long seed, unsigned long long offset,
-                      float* ctx, float* probs, sed_stream_t stream);
+                      const unsigned long long* philox_state, float* ctx, float* probs, sed_stream_t stream);
 int sed_attention_bwd(const float* q, const float* k, const float* v, int ldq, int ldk, int ldv, int B, int T, int H,
                       int d, float temperature, float p_drop, unsigned long long seed, unsigned long long offset,
-                      const float* dctx, const float* probs, float* dq, float* dk, float* dv,
-                      sed_stream_t stream);
+                      const unsigned long long* philox_state, const float* dctx, const float* probs, float* dq, float* dk,
+                      float* dv, sed_stream_t stream);
 /* y = relu(dropout_p(x)) (models.py:664) and its backward dx = dy * [y > 0] / (1 - p). */
 int sed_dropout_relu_fwd(const float* x, long long n, float p_drop, unsigned long long seed, unsigned long long offset,
-                         float* y, sed_stream_t stream);
+                         const unsigned long long* philox_state, float* y, sed_stream_t stream);
 int sed_dropout_relu_bwd(const float* dy, const float* y, long long n, float p_drop, float* dx, sed_stream_t stream);
 
 /* ---- frame-wise probabilities -> sound events (onset, offset frame indices), bit-exact ------------

@@ -77,9 +77,9 @@ SIGNATURES = {
     'sed_gru_workspace_bytes': [I, I, I],
     'sed_gru_fwd': [P, P, P, P, P, P, I, I, I, P],
     'sed_gru_bwd': [P, P, P, P, P, P, P, P, P, P, P, I, I, I, P],
-    'sed_attention_fwd': [P, P, P, I, I, I, I, I, I, I, F, F, U, U, P, P, P],
-    'sed_attention_bwd': [P, P, P, I, I, I, I, I, I, I, F, F, U, U, P, P, P, P, P, P],
-    'sed_dropout_relu_fwd': [P, L, F, U, U, P, P],
+    'sed_attention_fwd': [P, P, P, I, I, I, I, I, I, I, F, F, U, U, P, P, P, P],
+    'sed_attention_bwd': [P, P, P, I, I, I, I, I, I, I, F, F, U, U, P, P, P, P, P, P, P],
+    'sed_dropout_relu_fwd': [P, L, F, U, U, P, P, P],
     'sed_dropout_relu_bwd': [P, P, L, F, P, P],
     'sed_vad_count': [P, P, I, I, I, P, P, P, P, P, P, P, P],
     'sed_vad_fill': [P, P, I, I, I, P, P, P, P, P, P, P, P],

@@ -23,15 +23,40 @@ F32 = torch.float32
 
 
 class MhaCtx(object):
-    __slots__ = ('x2d', 'qkv', 'probs', 'ctx2d', 'y', 'shape', 'p_att', 'p_out', 'seed', 'off_att')
+    __slots__ = ('x2d', 'qkv', 'probs', 'ctx2d', 'y', 'shape', 'p_att', 'p_out', 'seed', 'off_att', 'state_att')
+
+
+class PhiloxIndirect(object):
+    """Generator state through device memory, for CUDA-graph replay (trainer.FusedTrainer): while ``active`` is set the
+    kernels read {seed, offset base} from the two int64 device words ``state`` at run time and the offsets handed out here
+    are RELATIVE to the step's base (``blocks`` counts the Philox blocks the step has consumed so far); the trainer writes
+    the generator's current (seed, offset) into ``state`` before every replay and advances the generator by ``blocks``."""
+    __slots__ = ('state', 'blocks')
+
+    def __init__(self, dev):
+        self.state = torch.zeros(2, dtype=torch.int64, device=dev)
+        self.blocks = 0
+
+
+INDIRECT = None        # a PhiloxIndirect while a step is captured / run through device-side generator state
+
+
+def _generator(dev):
+    return torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()]
 
 
 def _philox_state(dev, n):
-    """(seed, offset) from torch's CUDA generator of ``dev``; advances it by n draws."""
-    gen = torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()]
+    """(seed, offset in Philox blocks, device state pointer or 0) for n draws.  Direct mode: from torch's CUDA generator
+    of ``dev``, which advances by n draws.  Indirect mode (INDIRECT set): offsets relative to the step's base."""
+    blocks = (n + 3) // 4
+    if INDIRECT is not None:
+        off = INDIRECT.blocks
+        INDIRECT.blocks += blocks
+        return 0, off, INDIRECT.state.data_ptr()
+    gen = _generator(dev)
     seed, off = gen.initial_seed(), gen.get_offset()
-    gen.set_offset(off + 4 * ((n + 3) // 4))
-    return seed & 0xFFFFFFFFFFFFFFFF, off // 4
+    gen.set_offset(off + 4 * blocks)
+    return seed & 0xFFFFFFFFFFFFFFFF, off // 4, 0
 
 
 def _check(mh):
@@ -53,23 +78,24 @@ def multihead_forward(mh, feat, training, keep):
     ld = 3 * h * d
     p_att = float(mh.attention.dropout.p) if training else 0.0
     p_out = float(mh.dropout.p) if training else 0.0
-    seed, off_att = _philox_state(dev, b * h * t * 128) if p_att > 0 else (0, 0)    # element index = score row * 128 + key
+    seed, off_att, st_att = _philox_state(dev, b * h * t * 128) if p_att > 0 else (0, 0, 0)   # element = score row * 128 + key
     ctx2d = torch.empty((b * t, h * d), dtype=F32, device=dev)
     probs = torch.empty((b, h, t, t), dtype=F32, device=dev) if keep else None
     temperature = float(mh.attention.temperature)
     with torch.cuda.device(dev):
         base = qkv.data_ptr()
         call('sed_attention_fwd', base, base + 4 * h * d, base + 8 * h * d, ld, ld, ld, b, t, h, d, temperature,
-             p_att, seed, off_att, ctx2d.data_ptr(), ptr(probs), stream_of(feat))
+             p_att, seed, off_att, st_att, ctx2d.data_ptr(), ptr(probs), stream_of(feat))
         o = gemm.linear_x3(ctx2d, mh.fc.weight, mh.fc.bias)                           # (B*T, d_model)
-        seed_o, off_o = _philox_state(dev, o.numel()) if p_out > 0 else (0, 0)
+        seed_o, off_o, st_o = _philox_state(dev, o.numel()) if p_out > 0 else (0, 0, 0)
         y = torch.empty_like(o)
-        call('sed_dropout_relu_fwd', o.data_ptr(), o.numel(), p_out, seed_o, off_o, y.data_ptr(), stream_of(feat))
+        call('sed_dropout_relu_fwd', o.data_ptr(), o.numel(), p_out, seed_o, off_o, st_o, y.data_ptr(), stream_of(feat))
     mctx = None
     if keep:
         mctx = MhaCtx()
         mctx.x2d, mctx.qkv, mctx.probs, mctx.ctx2d, mctx.y = x2d, qkv, probs, ctx2d, y
         mctx.shape, mctx.p_att, mctx.p_out, mctx.seed, mctx.off_att = (b, t, c, h, d), p_att, p_out, seed, off_att
+        mctx.state_att = st_att
     return y.view(b, t, mh.fc.weight.shape[0]), mctx
 
 
@@ -94,7 +120,7 @@ def multihead_backward(mh, mctx, dfeat, grad_of):
         dqkv = torch.empty((b * t, ld), dtype=F32, device=dev)
         qb, gb = mctx.qkv.data_ptr(), dqkv.data_ptr()
         call('sed_attention_bwd', qb, qb + 4 * h * d, qb + 8 * h * d, ld, ld, ld, b, t, h, d,
-             float(mh.attention.temperature), mctx.p_att, mctx.seed, mctx.off_att, dctx.data_ptr(),
+             float(mh.attention.temperature), mctx.p_att, mctx.seed, mctx.off_att, mctx.state_att, dctx.data_ptr(),
              mctx.probs.data_ptr(), gb, gb + 4 * h * d, gb + 8 * h * d, s)
         dqkv16, x16 = tcconv.to_bf16(dqkv), tcconv.to_bf16(mctx.x2d)
         db = torch.empty(ld, dtype=F32, device=dev)

@@ -9,7 +9,9 @@ namespace {
 
 // y = relu(dropout_p(x)) elementwise (models.py:664: F.relu_(self.dropout(self.fc(output))))
 __global__ void dropout_relu_fwd_kernel(const float* __restrict__ x, long long n, float p, unsigned long long seed,
-                                        unsigned long long offset, float* __restrict__ y) {
+                                        unsigned long long offset, const unsigned long long* __restrict__ state,
+                                        float* __restrict__ y) {
+  if (state != nullptr) { seed = state[0]; offset += state[1]; }
   const float keep_scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float v = x[i];
@@ -33,11 +35,11 @@ using namespace sed;
 extern "C" {
 
 int sed_dropout_relu_fwd(const float* x, long long n, float p_drop, unsigned long long seed, unsigned long long offset,
-                         float* y, sed_stream_t stream) {
+                         const unsigned long long* philox_state, float* y, sed_stream_t stream) {
   SED_REQUIRE(x && y && n >= 0 && p_drop >= 0.f && p_drop < 1.f, "sed_dropout_relu_fwd: bad arguments");
   if (n == 0) return 0;
   const int grid = (int)min((n + 255) / 256, (long long)sm_count() * 16);
-  dropout_relu_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, p_drop, seed, offset, y);
+  dropout_relu_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, p_drop, seed, offset, philox_state, y);
   SED_LAUNCH_CHECK("dropout_relu_fwd_kernel");
   return 0;
 }

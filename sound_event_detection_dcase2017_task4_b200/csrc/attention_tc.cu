@@ -42,6 +42,7 @@ struct AttParams {
   float inv_temp;
   float p_drop;                                       // 0 = no dropout
   unsigned long long seed, offset;
+  const unsigned long long* state;                    // optional device words {seed, offset base}: see sed_b200.h
 };
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const __nv_bfloat16* p) {
@@ -150,6 +151,7 @@ __device__ __forceinline__ void keep_pair(const AttParams& p, long long srow, in
 // ctx (B*T, H*64) fp32; probs (B, H, T, T) fp32 softmax output BEFORE dropout (may be nullptr)
 __global__ void __launch_bounds__(kAttThreads, 1)
 attention_tc_fwd_kernel(AttParams p, float* __restrict__ ctx, float* __restrict__ probs) {
+  if (p.state != nullptr) { p.seed = p.state[0]; p.offset += p.state[1]; }
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __nv_bfloat16* sQh = reinterpret_cast<__nv_bfloat16*>(smem_raw);
   __nv_bfloat16* sQl = sQh + kTile;
@@ -252,6 +254,7 @@ attention_tc_fwd_kernel(AttParams p, float* __restrict__ ctx, float* __restrict_
 __global__ void __launch_bounds__(kAttThreads, 1)
 attention_tc_bwd_kernel(AttParams p, const float* __restrict__ dctx, const float* __restrict__ probs,
                         float* __restrict__ dq, float* __restrict__ dk, float* __restrict__ dv) {
+  if (p.state != nullptr) { p.seed = p.state[0]; p.offset += p.state[1]; }
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __nv_bfloat16* sQh = reinterpret_cast<__nv_bfloat16*>(smem_raw);
   __nv_bfloat16* sQl = sQh + kTile;
@@ -431,12 +434,12 @@ extern "C" {
 
 int sed_attention_fwd(const float* q, const float* k, const float* v, int ldq, int ldk, int ldv, int B, int T, int H,
                       int d, float temperature, float p_drop, unsigned long long seed, unsigned long long offset,
-                      float* ctx, float* probs, sed_stream_t stream) {
+                      const unsigned long long* philox_state, float* ctx, float* probs, sed_stream_t stream) {
   if (int rc = check_att("sed_attention_fwd", q, k, v, ldq, ldk, ldv, B, T, H, d)) return rc;
   SED_REQUIRE(ctx && aligned(ctx, 8), "sed_attention_fwd: null / misaligned output");
   SED_REQUIRE(p_drop >= 0.f && p_drop < 1.f && temperature > 0.f, "sed_attention_fwd: bad scalars");
   if (B == 0) return 0;
-  AttParams p{q, k, v, ldq, ldk, ldv, B, T, H, 1.0f / temperature, p_drop, seed, offset};
+  AttParams p{q, k, v, ldq, ldk, ldv, B, T, H, 1.0f / temperature, p_drop, seed, offset, philox_state};
   const size_t smem = sizeof(__nv_bfloat16) * (size_t)(6 * kTile);
   SED_CUDA(cudaFuncSetAttribute(attention_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   attention_tc_fwd_kernel<<<B * H, kAttThreads, smem, (cudaStream_t)stream>>>(p, ctx, probs);
@@ -446,12 +449,13 @@ int sed_attention_fwd(const float* q, const float* k, const float* v, int ldq, i
 
 int sed_attention_bwd(const float* q, const float* k, const float* v, int ldq, int ldk, int ldv, int B, int T, int H,
                       int d, float temperature, float p_drop, unsigned long long seed, unsigned long long offset,
-                      const float* dctx, const float* probs, float* dq, float* dk, float* dv, sed_stream_t stream) {
+                      const unsigned long long* philox_state, const float* dctx, const float* probs, float* dq, float* dk,
+                      float* dv, sed_stream_t stream) {
   if (int rc = check_att("sed_attention_bwd", q, k, v, ldq, ldk, ldv, B, T, H, d)) return rc;
   SED_REQUIRE(dctx && probs && dq && dk && dv, "sed_attention_bwd: null pointer");
   SED_REQUIRE(aligned(dctx, 16) && aligned(dq, 8) && aligned(dk, 8) && aligned(dv, 8), "sed_attention_bwd: misaligned pointer");
   if (B == 0) return 0;
-  AttParams p{q, k, v, ldq, ldk, ldv, B, T, H, 1.0f / temperature, p_drop, seed, offset};
+  AttParams p{q, k, v, ldq, ldk, ldv, B, T, H, 1.0f / temperature, p_drop, seed, offset, philox_state};
   const size_t smem = sizeof(__nv_bfloat16) * (size_t)(8 * kTile) + sizeof(float) * kMaxT;
   SED_CUDA(cudaFuncSetAttribute(attention_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   attention_tc_bwd_kernel<<<B * H, kAttThreads, smem, (cudaStream_t)stream>>>(p, dctx, probs, dq, dk, dv);

@@ -74,8 +74,10 @@ class FusedTrainer(object):
         # tensors that are refreshed before every replay.  With world_size > 1 the graph ends before the collective
         # (capturing the NCCL all-reduce inside the two-stream graph hung in a 2-GPU trial): forward + backward replay
         # as one graph, then the all-reduce and the one Adam kernel are launched eagerly.
-        # (the multi-head models draw their dropout offsets on the host per step and stay on eager launches)
-        self.use_graph = bool(use_graph) and getattr(model, 'temporal_kind', None) != 'mha'
+        # The multi-head models' dropout draws (seed, offset) from torch's CUDA generator on the host: under replay the
+        # kernels read them from two device words instead (attention.PhiloxIndirect), refreshed before every replay.
+        self.use_graph = bool(use_graph)
+        self._philox = None
         self._graphs = {}
         self._pool = None
         self._eager_steps = 0
@@ -149,22 +151,40 @@ class FusedTrainer(object):
         entry['ts'].copy_(torch.from_numpy(ts))
         entry['fs'].copy_(torch.from_numpy(fs))
         entry['bc'].copy_(torch.from_numpy(bc))
+        mha = getattr(model, 'temporal_kind', None) == 'mha'
+        if mha:
+            from . import attention
+            if self._philox is None:
+                self._philox = attention.PhiloxIndirect(dev)
+            gen = attention._generator(dev)
+            seed, off = gen.initial_seed(), gen.get_offset()
+            self._philox.state.copy_(torch.tensor([seed - (1 << 64) if seed >= (1 << 63) else seed, off // 4],
+                                                  dtype=torch.int64))
         if 'graph' not in entry:
             n0 = _lib.launch_count()
             count0 = self.step_count
             g = torch.cuda.CUDAGraph()
             if self._pool is None:
                 self._pool = torch.cuda.graph_pool_handle()   # all graphs of this trainer share one memory pool: they
-            with torch.cuda.graph(g, pool=self._pool):        # are replayed one at a time and their outputs are read first
-                if self.world_size == 1:
-                    loss = self._step_body(wave, target, lam, stripes=(entry['ts'], entry['fs']), bias_corr=entry['bc'])
-                else:
-                    loss = self._forward_backward(wave, target, lam, stripes=(entry['ts'], entry['fs']))
+            if mha:
+                attention.INDIRECT, self._philox.blocks = self._philox, 0
+            try:
+                with torch.cuda.graph(g, pool=self._pool):    # are replayed one at a time and their outputs are read first
+                    if self.world_size == 1:
+                        loss = self._step_body(wave, target, lam, stripes=(entry['ts'], entry['fs']), bias_corr=entry['bc'])
+                    else:
+                        loss = self._forward_backward(wave, target, lam, stripes=(entry['ts'], entry['fs']))
+            finally:
+                if mha:
+                    attention.INDIRECT = None
+            entry['philox_blocks'] = self._philox.blocks if mha else 0
             self.step_count = count0                       # capture executed nothing
             entry['graph'], entry['loss'], entry['out'] = g, loss, self.last_output
             self.graph_launches = _lib.launch_count() - n0
             self._graphs[key] = entry
         entry['graph'].replay()
+        if mha:                                            # the draws of this step, as the eager path would have advanced
+            gen.set_offset(off + 4 * entry['philox_blocks'])
         if self.world_size == 1:
             self.step_count += 1
         else:

@@ -69,7 +69,7 @@ def test_attention_kernel_exact_fp32_parts():
     ctx = torch.empty(B * T, H * d, device='cuda')
     probs = torch.empty(B, H, T, T, device='cuda')
     base, ld = qkv.data_ptr(), 3 * H * d
-    call('sed_attention_fwd', base, base + 4 * H * d, base + 8 * H * d, ld, ld, ld, B, T, H, d, 8.0, 0.0, 0, 0,
+    call('sed_attention_fwd', base, base + 4 * H * d, base + 8 * H * d, ld, ld, ld, B, T, H, d, 8.0, 0.0, 0, 0, 0,
          ctx.data_ptr(), probs.data_ptr(), stream_of(qkv))
     assert torch.allclose(ctx, ctx_ref, rtol=1e-4, atol=1e-5)
     assert torch.allclose(probs, att, rtol=1e-4, atol=1e-7)
@@ -77,7 +77,7 @@ def test_attention_kernel_exact_fp32_parts():
     ctx_ref.backward(dctx)
     dqkv = torch.empty_like(qkv)
     gb = dqkv.data_ptr()
-    call('sed_attention_bwd', base, base + 4 * H * d, base + 8 * H * d, ld, ld, ld, B, T, H, d, 8.0, 0.0, 0, 0,
+    call('sed_attention_bwd', base, base + 4 * H * d, base + 8 * H * d, ld, ld, ld, B, T, H, d, 8.0, 0.0, 0, 0, 0,
          dctx.data_ptr(), probs.data_ptr(), gb, gb + 4 * H * d, gb + 8 * H * d, stream_of(qkv))
     assert torch.allclose(dqkv, ref_in.grad, rtol=1e-3, atol=1e-5)
 
@@ -89,15 +89,21 @@ def test_dropout_statistics_and_determinism():
     n = 1 << 20
     x = torch.ones(n, device='cuda')
     y = torch.empty_like(x)
-    call('sed_dropout_relu_fwd', x.data_ptr(), n, 0.2, 1234, 0, y.data_ptr(), stream_of(x))
+    call('sed_dropout_relu_fwd', x.data_ptr(), n, 0.2, 1234, 0, 0, y.data_ptr(), stream_of(x))
     kept = (y > 0).float().mean().item()
     assert abs(kept - 0.8) < 3e-3
     assert torch.all((y == 0) | ((y - 1.25).abs() < 1e-6))
     y2 = torch.empty_like(x)
-    call('sed_dropout_relu_fwd', x.data_ptr(), n, 0.2, 1234, 0, y2.data_ptr(), stream_of(x))
+    call('sed_dropout_relu_fwd', x.data_ptr(), n, 0.2, 1234, 0, 0, y2.data_ptr(), stream_of(x))
     assert torch.equal(y, y2)
-    call('sed_dropout_relu_fwd', x.data_ptr(), n, 0.2, 1235, 0, y2.data_ptr(), stream_of(x))
+    call('sed_dropout_relu_fwd', x.data_ptr(), n, 0.2, 1235, 0, 0, y2.data_ptr(), stream_of(x))
     assert not torch.equal(y, y2)
+    # generator state through device memory (CUDA-graph replay): {seed, offset base} words + relative offset
+    state = torch.tensor([1234, 5], dtype=torch.int64, device='cuda')
+    y3, y4 = torch.empty_like(x), torch.empty_like(x)
+    call('sed_dropout_relu_fwd', x.data_ptr(), n, 0.2, 999, 3, state.data_ptr(), y3.data_ptr(), stream_of(x))
+    call('sed_dropout_relu_fwd', x.data_ptr(), n, 0.2, 1234, 8, 0, y4.data_ptr(), stream_of(x))
+    assert torch.equal(y3, y4)
     dx = torch.empty_like(x)
     call('sed_dropout_relu_bwd', x.data_ptr(), y.data_ptr(), n, 0.2, dx.data_ptr(), stream_of(x))
     assert torch.equal(dx, y)                                 # dy = 1: dx = mask / (1 - p) = y

@@ -277,10 +277,12 @@ def test_eval_mode_is_differentiable_like_the_reference(name):
         assert err <= max(3e-2, 2.0 * band + 2e-2) and cos >= 0.9, (k, err, band, cos)
 
 
-def test_cuda_graph_replay_equals_eager_steps():
-    """FusedTrainer(use_graph=True) captures the step once per input-buffer set and replays it; SpecAugment stripes and
-    Adam's bias corrections reach the replay through device memory.  Loss trajectory, parameters and optimizer state
-    must be BIT-identical to eager launches (same kernels, same order)."""
+@pytest.mark.parametrize('name', ['Cnn_9layers_Gru_FrameAtt', 'Cnn_9layers_Transformer_FrameAvg'])
+def test_cuda_graph_replay_equals_eager_steps(name):
+    """FusedTrainer(use_graph=True) captures the step once per input-buffer set and replays it; SpecAugment stripes,
+    Adam's bias corrections and (Transformer variants) the dropout generator state reach the replay through device
+    memory.  Loss trajectory, parameters, optimizer state and the CUDA generator's final offset must be BIT-identical
+    to eager launches (same kernels, same order, same Philox counters)."""
     from oracle import sed
     from sound_event_detection_dcase2017_task4_b200 import models
     from sound_event_detection_dcase2017_task4_b200.trainer import FusedTrainer
@@ -290,13 +292,17 @@ def test_cuda_graph_replay_equals_eager_steps():
     runs = []
     for use_graph in (False, True):
         torch.manual_seed(0)
-        model = models.Cnn_9layers_Gru_FrameAtt(*CTOR).cuda().train()
+        model = getattr(models, name)(*CTOR).cuda().train()
         tr = FusedTrainer(model, lr=1e-3, use_graph=use_graph)
         torch.manual_seed(9)
         losses = [float(tr.step(wave, target, lam)) for _ in range(7)]
         torch.cuda.synchronize()
-        runs.append((losses, tr.flat_param.clone(), tr.max_exp_avg_sq.clone(), int(model.bn0.num_batches_tracked), tr))
+        runs.append((losses, tr.flat_param.clone(), tr.max_exp_avg_sq.clone(), int(model.bn0.num_batches_tracked), tr,
+                     torch.cuda.default_generators[0].get_offset()))
     assert runs[1][4].use_graph and runs[1][4].graph_launches > 50 and len(runs[1][4]._graphs) == 1
     assert runs[0][0] == runs[1][0], (runs[0][0], runs[1][0])
     assert torch.equal(runs[0][1], runs[1][1]) and torch.equal(runs[0][2], runs[1][2])
     assert runs[0][3] == runs[1][3] == 7
+    assert runs[0][5] == runs[1][5]
+    if 'Transformer' in name:
+        assert len(set(runs[1][0])) == 7                       # a fresh dropout mask per replay, not the captured one
