@@ -245,9 +245,13 @@ int sed_gru_fwd(const float* gx, const float* w_hh, const float* b_hh, float* ou
                 int B, int T, int H, sed_stream_t stream);
 /* dgx_bf16 / dgh_bf16 / hprev_bf16: optional (all three or none, H = 256 only) bf16 copies of the three outputs,
  * written by the same kernel: the operands of the weight-gradient GEMMs that follow (saves three conversion passes). */
+/* bias_partial: optional (H = 256 only) fp32 (sed_gru_bwd_bias_rows(B), 2, 2, 3H) partial sums over (batch, time) of dgx
+ * ([.][0][direction]) and dgh ([.][1][direction]): summed over the first dimension (sed_reduce_partials) they are the
+ * gradients of b_ih and b_hh -- saves the two column-sum passes over dgx / dgh. */
+int sed_gru_bwd_bias_rows(int B);
 int sed_gru_bwd(const float* dout, const float* out, const float* gates, const float* w_hh, float* carry,
-                float* dgx, float* dgh, float* hprev, void* dgx_bf16, void* dgh_bf16, void* hprev_bf16, int B, int T,
-                int H, sed_stream_t stream);
+                float* dgx, float* dgh, float* hprev, void* dgx_bf16, void* dgh_bf16, void* hprev_bf16,
+                float* bias_partial, int B, int T, int H, sed_stream_t stream);
 
 /* ---- scaled-dot-product attention of MultiHead (pytorch/models.py:596-608 inside :641-665) -------
  * q/k/v: fp32 (B*T, ld) row-major, head h in columns [h*64, h*64+64): the outputs of the w_qs / w_ks /

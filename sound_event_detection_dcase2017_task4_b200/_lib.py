@@ -76,7 +76,8 @@ SIGNATURES = {
     'sed_colsum_f32': [P, L, I, P, P],
     'sed_gru_workspace_bytes': [I, I, I],
     'sed_gru_fwd': [P, P, P, P, P, P, I, I, I, P],
-    'sed_gru_bwd': [P, P, P, P, P, P, P, P, P, P, P, I, I, I, P],
+    'sed_gru_bwd_bias_rows': [I],
+    'sed_gru_bwd': [P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, P],
     'sed_attention_fwd': [P, P, P, I, I, I, I, I, I, I, F, F, U, U, P, P, P, P],
     'sed_attention_bwd': [P, P, P, I, I, I, I, I, I, I, F, F, U, U, P, P, P, P, P, P, P],
     'sed_dropout_relu_fwd': [P, L, F, U, U, P, P, P],

@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(kPThreads, 1)
 gru_bwd_persistent_kernel(const float* __restrict__ dout, const float* __restrict__ out, const float* __restrict__ gates,
                           const float* __restrict__ Whh, float* __restrict__ dGx, float* dGh,
                           float* __restrict__ Hprev, __nv_bfloat16* __restrict__ dGx16, __nv_bfloat16* __restrict__ dGh16,
-                          __nv_bfloat16* __restrict__ Hprev16, GruPersist q) {
+                          __nv_bfloat16* __restrict__ Hprev16, float* __restrict__ bias_partial, GruPersist q) {
   extern __shared__ __align__(16) uint8_t smem_gru[];
   __nv_bfloat16* sWh = reinterpret_cast<__nv_bfloat16*>(smem_gru);      // [256][kLdB]  W_hh[g H + u0 + jl][n] at [n][g 32 + jl], hi
   __nv_bfloat16* sWl = sWh + kPH * kLdB;                                //              lo
@@ -447,6 +447,7 @@ gru_bwd_persistent_kernel(const float* __restrict__ dout, const float* __restric
   const int jl = oct * 8 + tig * 2;                                     // this thread's units: u0 + jl, u0 + jl + 1
   const int j = u0 + jl;
   float dhz[2][2] = {{0.f, 0.f}, {0.f, 0.f}};                           // dh * z of the previous step (own units)
+  float bsum[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};  // bias gradients: sum over (rows, t) of dr, dz, dn, dn*r
   for (int bs = 0; bs < T; ++bs) {
     const int tt = d == 0 ? T - 1 - bs : bs;
     const int tp = d == 0 ? tt - 1 : tt + 1;
@@ -519,6 +520,7 @@ gru_bwd_persistent_kernel(const float* __restrict__ dout, const float* __restric
           drp[u] = dnp[u] * ghn * r * (1.f - r);
           dnr[u] = dnp[u] * r;
           dhz[rr][u] = dh * z;
+          bsum[0][u] += drp[u]; bsum[1][u] += dzp[u]; bsum[2][u] += dnp[u]; bsum[3][u] += dnr[u];
         }
         float* gx = dGx + (bt * 2 + d) * 3 * H + j;
         float* gh = dGh + (bt * 2 + d) * 3 * H + j;
@@ -604,6 +606,32 @@ gru_bwd_persistent_kernel(const float* __restrict__ dout, const float* __restric
           if (b0 + row0 + rr * 8 < B)
             st_relaxed_v4(xc + rr * 8 * 16, __float_as_uint(acc[nt][rr * 2]), tg, __float_as_uint(acc[nt][rr * 2 + 1]), tg);
       }
+    }
+  }
+  // ---- bias gradients db_ih = sum dGx, db_hh = sum dGh over (batch, time): this thread's two rows are summed, the
+  //      eight row lanes of the warp follow (fixed shuffle tree), one partial row per (batch tile, half):
+  //      bias_partial[(tile * 2 + half)][ih | hh][direction][3H]   (summed in row order by sed_reduce_partials)
+  if (bias_partial != nullptr) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        float v = bsum[k][u];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        bsum[k][u] = v;
+      }
+    if (gid == 0) {
+      const long long prow = (long long)(q.b_base / kPB + blockIdx.y) * 2 + mt;
+      float* pih = bias_partial + ((prow * 2 + 0) * 2 + d) * 3 * H + j;
+      float* phh = bias_partial + ((prow * 2 + 1) * 2 + d) * 3 * H + j;
+      *reinterpret_cast<float2*>(pih) = make_float2(bsum[0][0], bsum[0][1]);
+      *reinterpret_cast<float2*>(pih + H) = make_float2(bsum[1][0], bsum[1][1]);
+      *reinterpret_cast<float2*>(pih + 2 * H) = make_float2(bsum[2][0], bsum[2][1]);
+      *reinterpret_cast<float2*>(phh) = make_float2(bsum[0][0], bsum[0][1]);
+      *reinterpret_cast<float2*>(phh + H) = make_float2(bsum[1][0], bsum[1][1]);
+      *reinterpret_cast<float2*>(phh + 2 * H) = make_float2(bsum[3][0], bsum[3][1]);
     }
   }
 }
@@ -720,14 +748,18 @@ int sed_gru_fwd(const float* gx, const float* w_hh, const float* b_hh, float* ou
   return 0;
 }
 
+int sed_gru_bwd_bias_rows(int B) { return 2 * ((B + kPB - 1) / kPB); }
+
 int sed_gru_bwd(const float* dout, const float* out, const float* gates, const float* w_hh, float* carry /* (2,2,B,H) */,
-                float* dgx, float* dgh, float* hprev, void* dgx_bf16, void* dgh_bf16, void* hprev_bf16, int B, int T, int H,
-                sed_stream_t stream) {
+                float* dgx, float* dgh, float* hprev, void* dgx_bf16, void* dgh_bf16, void* hprev_bf16, float* bias_partial,
+                int B, int T, int H, sed_stream_t stream) {
   SED_REQUIRE(dout && out && gates && w_hh && carry && dgx && dgh && hprev, "sed_gru_bwd: null pointer");
   const bool want16 = dgx_bf16 || dgh_bf16 || hprev_bf16;
   SED_REQUIRE(!want16 || (dgx_bf16 && dgh_bf16 && hprev_bf16 && H == kPH),
               "sed_gru_bwd: the bf16 copies come all three or not at all, and only from the H = %d kernel", kPH);
   SED_REQUIRE(H % kHT == 0 && H % 4 == 0 && H <= 256, "sed_gru_bwd: hidden size %d unsupported", H);
+  SED_REQUIRE(bias_partial == nullptr || H == kPH, "sed_gru_bwd: the bias-gradient partials come only from the H = %d kernel",
+              kPH);
   if (B == 0 || T == 0) return 0;
   if (H == kPH) {
     // dh never leaves registers; the scratch is the exchange area of the partial sums
@@ -737,7 +769,8 @@ int sed_gru_bwd(const float* dout, const float* out, const float* gates, const f
                                    a[0] = (void*)&dout; a[1] = (void*)&out; a[2] = (void*)&gates; a[3] = (void*)&w_hh;
                                    a[4] = (void*)&dgx; a[5] = (void*)&dgh; a[6] = (void*)&hprev;
                                    a[7] = (void*)&dgx_bf16; a[8] = (void*)&dgh_bf16; a[9] = (void*)&hprev_bf16;
-                                   return 10;
+                                   a[10] = (void*)&bias_partial;
+                                   return 11;
                                  });
   }
   const size_t smem = sizeof(float) * (size_t)(3 * H * kHT + kBT * 3 * H + kBT * kHT);

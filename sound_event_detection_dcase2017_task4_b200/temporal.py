@@ -62,20 +62,26 @@ def gru_backward(gru, ctx, dout, grad_of):
         dgx16 = torch.empty(dgx.shape, dtype=torch.bfloat16, device=dev)
         dgh16 = torch.empty(dgh.shape, dtype=torch.bfloat16, device=dev)
         hp16 = torch.empty(hprev.shape, dtype=torch.bfloat16, device=dev)
+        # ... and per-(batch tile, half) partial sums of dGx / dGh over (batch, time): the bias gradients
+        bias_partial = torch.empty((_lib.lib().sed_gru_bwd_bias_rows(b), 2, 2 * 3 * h), dtype=F32, device=dev)
     with torch.cuda.device(dev):
         call('sed_gru_bwd', dout.data_ptr(), ctx.out.data_ptr(), ctx.gates.data_ptr(), w_hh.data_ptr(),
              carry.data_ptr(), dgx.data_ptr(), dgh.data_ptr(), hprev.data_ptr(),
              dgx16.data_ptr() if fused16 else 0, dgh16.data_ptr() if fused16 else 0, hp16.data_ptr() if fused16 else 0,
-             b, t, h, stream_of(dout))
+             bias_partial.data_ptr() if fused16 else 0, b, t, h, stream_of(dout))
     if not fused16:
         dgx16, dgh16, hp16 = tcconv.to_bf16(dgx), tcconv.to_bf16(dgh), tcconv.to_bf16(hprev)
     # X as bf16: the hi third of the [hi | lo | hi] split the forward projection already made (row stride 3 * C)
     x16 = ctx.x3 if ctx.x3 is not None else tcconv.to_bf16(ctx.x2d)
     # weight gradients: dW_ih[d] = dGx_d^T X ; dW_hh[d] = dGh_d^T Hprev_d ; biases = column sums
-    db_ih = torch.empty(2 * 3 * h, dtype=F32, device=dev)
-    db_hh = torch.empty(2 * 3 * h, dtype=F32, device=dev)
-    gemm.colsum(dgx, db_ih)
-    gemm.colsum(dgh, db_hh)
+    if fused16:
+        db = ops.reduce_partials(bias_partial, torch.empty((2, 2 * 3 * h), dtype=F32, device=dev))
+        db_ih, db_hh = db[0], db[1]
+    else:
+        db_ih = torch.empty(2 * 3 * h, dtype=F32, device=dev)
+        db_hh = torch.empty(2 * 3 * h, dtype=F32, device=dev)
+        gemm.colsum(dgx, db_ih)
+        gemm.colsum(dgh, db_hh)
     for d, sfx in enumerate(('', '_reverse')):
         g = grad_of(getattr(gru, 'weight_ih_l0' + sfx))
         if g is not None:
