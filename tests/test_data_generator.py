@@ -78,3 +78,28 @@ def test_batcher_matches_sampler_plus_dataset(tmp_path):
         assert got['waveform'].dtype == np.int16
         assert np.array_equal((got['waveform'] / 32767.).astype(np.float32), want['waveform'])
         assert np.array_equal(got['target'], want['target'])
+
+
+def test_clip_store_gather_threaded_equals_rows(tmp_path):
+    """ClipStore.gather copies rows with positional reads on a thread pool, in request order, repeats included, into
+    caller-provided buffers or fresh arrays; targets come back as fp32."""
+    import numpy as np
+    from sound_event_detection_dcase2017_task4_b200 import data_generator as dg
+    rs = np.random.RandomState(3)
+    n, samples = 41, 120000                                   # 41 x 120000 int16 > 4 M elements: the threaded path
+    wave = rs.randint(-32768, 32767, size=(n, samples)).astype(np.int16)
+    target = (rs.rand(n, 17) > 0.7).astype(np.uint8)
+    strong = (rs.rand(n, 11, 17) > 0.7).astype(np.uint8)
+    store = dg.ClipStore.write(str(tmp_path / 'store'), ['a%d' % i for i in range(n)], wave, target, strong)
+    idx = rs.randint(0, n, size=37)
+    idx[5] = idx[6]                                           # a repeated clip
+    for threads in (1, 4):
+        got = store.gather(idx, threads=threads)
+        assert got['waveform'].dtype == np.int16 and np.array_equal(got['waveform'], wave[idx])
+        assert got['target'].dtype == np.float32 and np.array_equal(got['target'], target[idx].astype(np.float32))
+        assert np.array_equal(got['strong_target'], strong[idx].astype(np.float32))
+        assert list(got['audio_name']) == ['a%d' % i for i in idx]
+        out = {'waveform': np.full((37, samples), 7, dtype=np.int16), 'target': np.zeros((37, 17), dtype=np.float32)}
+        got = store.gather(idx, out=out, threads=threads)
+        assert got['waveform'] is out['waveform'] and np.array_equal(out['waveform'], wave[idx])
+        assert np.array_equal(out['target'], target[idx].astype(np.float32))
