@@ -115,10 +115,10 @@ _SIDE_STREAMS = {}
 # for co-residency (csrc/bnpool.cu "backward fast paths", csrc/conv_wgrad_tc.cu kWgradSmemBudget).
 OVERLAP_WGRAD = True
 # Layers (index into ctx.layers, 0 = block1.conv1) whose weight gradient may go to the side stream.  The 64 -> 64 layer
-# (index 1) is excluded: its weight-gradient kernel is bound by shared-memory operand reads (SS-mode tcgen05.mma with
-# N = 64), and the BatchNorm-backward loads of layer 0 that it would run beside go through the same L1/shared-memory
-# SRAM -- measured (tools/timeline.py) the reduce pass took 2.4 ms beside it vs 0.7 ms alone, a net loss.
-OVERLAP_LAYERS = frozenset((2, 3, 4, 5, 6, 7))
+# (index 1) was excluded while its weight-gradient kernel was bound by shared-memory operand reads (N = 64: beside it the
+# BatchNorm reduce pass of layer 0 took 2.4 ms instead of 0.7, tools/timeline.py); with the kh taps stacked in N
+# (csrc/conv_wgrad_tc.cu) it is included again: 28.51 -> 28.42, 28.69 -> 28.63 ms/step in a same-box A/B (tools/ab_step.py).
+OVERLAP_LAYERS = frozenset((1, 2, 3, 4, 5, 6, 7))
 # Fold the reduction pass of each BatchNorm backward into the epilogue of the data-gradient kernel that produces its dA
 # (sed_conv3x3_tc_dgrad_bnr).  Correct (tests/test_gpu_conv.py) but measured SLOWER on B200 at batch 256
 # (tools/ab_step.py: 42.1 vs 40.1 ms/step): the 8 epilogue warps cannot hide the HBM latency of the y reads that the
