@@ -164,8 +164,8 @@ gru_bwd_step_kernel(const float* __restrict__ dout, const float* __restrict__ ou
 // every produced value travels as {bf16 hi | bf16 lo, tag} in one 8-byte word of a double-buffered exchange area
 // (tag = step + 1, area zeroed by the host entry point): a consumer polls the words it needs until their tags match
 // and has data and "ready" in the same L2 round trip -- no fence, no atomic, and the hi/lo split the tensor-core
-// product needs is made once by the producer instead of by all 8 consumers.  8-byte accesses are single transactions;
-// the 16-byte vector accesses used here carry two such words and both tags are checked.
+// product needs is made once by the producer instead of by all 8 consumers.  The 16-byte vector accesses used here
+// carry two such 64-bit words (each single-copy atomic) and both tags are checked.
 // Slot reuse: slot (s & 1) is rewritten at step s + 2, which a producer only reaches after it has consumed step s + 1
 // from all 8 CTAs, and each of those wrote its step s + 1 values after all of its threads had finished reading step s.
 // The two 16-row halves of a CTA own disjoint batch rows, i.e. independent recurrences: while one half polls, the
@@ -179,14 +179,17 @@ constexpr int kPThreads = 256;
 __device__ __forceinline__ void half_barrier_sync(int bar_id) {
   asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 }
+// 16-byte exchange accesses as TWO 64-bit elements {value | tag << 32}: a naturally aligned 64-bit scalar element of a
+// vector access is single-copy atomic in the PTX memory model, so a value and its tag are always observed together.
 __device__ __forceinline__ uint4 ld_relaxed_v4(const uint4* p) {
-  uint4 v;
-  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-  return v;
+  unsigned long long a, b;
+  asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+  return make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
 }
 __device__ __forceinline__ void st_relaxed_v4(uint4* p, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
-  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+  const unsigned long long a = (unsigned long long)x | ((unsigned long long)y << 32);
+  const unsigned long long b = (unsigned long long)z | ((unsigned long long)w << 32);
+  asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
 // fp32 -> {bf16 hi (low half-word), bf16 lo = bf16(v - hi) (high half-word)}: the two terms of the operand split
 __device__ __forceinline__ uint32_t pack_hilo(float v) {
