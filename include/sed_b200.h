@@ -115,6 +115,13 @@ int sed_conv3x3_tc_wgrad(const void* dy, const void* x, float* slabs, int B, int
                          int Cout, sed_stream_t stream);
 int sed_conv_unpack_wgrad(const float* g_tap_major, int slabs, long long slab_stride, int Cout, int Cin,
                           float* grad_oihw, int accumulate, sed_stream_t stream);
+/* The two above for up to 8 layers in ONE launch each (arrays of `layers` entries on the host; results bit-identical to
+ * the per-layer entry points): weights are packed once at the top of the forward, the split-K slabs of all weight
+ * gradients are folded once at the end of the backward. */
+int sed_conv_pack_weights_multi(int layers, const float* const* w_oihw, const int* Cout, const int* Cin,
+                                void* const* fwd_pack, void* const* dgrad_pack, sed_stream_t stream);
+int sed_conv_unpack_wgrad_multi(int layers, const float* const* slabs, const int* n_slabs, const int* Cout, const int* Cin,
+                                float* const* grad_oihw, sed_stream_t stream);
 int sed_f32_to_bf16(const float* x, void* y, long long n, sed_stream_t stream);
 
 

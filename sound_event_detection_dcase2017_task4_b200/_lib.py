@@ -38,6 +38,8 @@ SIGNATURES = {
     'sed_conv3x3_tc_wgrad_use_pairs': [I],
     'sed_conv3x3_tc_wgrad': [P, P, P, I, I, I, I, I, P],
     'sed_conv_unpack_wgrad': [P, I, L, I, I, P, I, P],
+    'sed_conv_pack_weights_multi': [I, P, P, P, P, P, P],
+    'sed_conv_unpack_wgrad_multi': [I, P, P, P, P, P, P],
     'sed_f32_to_bf16': [P, P, L, P],
     'sed_bn_finalize': [P, I, I, D, P, P, F, F, P, P, P, P, P, P, P, P],
     'sed_bn_eval_affine': [P, P, P, P, F, I, P, P, P, P, P],

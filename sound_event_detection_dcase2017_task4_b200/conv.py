@@ -23,6 +23,74 @@ def pack_weights(w_oihw, want_fwd=True, want_dgrad=True):
     return fwd, dg
 
 
+def _c_array(ctype, values):
+    import ctypes
+    arr = (ctype * len(values))(*values)
+    return arr, ctypes.addressof(arr)
+
+
+def pack_weights_multi(ws, want_dgrad=True):
+    """[fp32 (Cout, Cin, 3, 3)] -> [(fwd bf16 [Cout, 9*Cin], dgrad bf16 [Cin, 9*Cout] or None)], ONE launch for all layers
+    (sed_conv_pack_weights_multi; same values as pack_weights per layer)."""
+    import ctypes
+    if not ws:
+        return []
+    dev = ws[0].device
+    ws = [w.detach().contiguous() for w in ws]
+    sizes = [w.numel() for w in ws]
+    pool = torch.empty(sum(sizes) * (2 if want_dgrad else 1), dtype=torch.bfloat16, device=dev)
+    packs, off = [], 0
+    for w, n in zip(ws, sizes):
+        cout, cin = w.shape[:2]
+        fwd = pool[off:off + n].view(cout, 9 * cin)
+        off += n
+        dg = None
+        if want_dgrad:
+            dg = pool[off:off + n].view(cin, 9 * cout)
+            off += n
+        packs.append((fwd, dg))
+    keep = [_c_array(ctypes.c_void_p, [w.data_ptr() for w in ws]),
+            _c_array(ctypes.c_int, [w.shape[0] for w in ws]), _c_array(ctypes.c_int, [w.shape[1] for w in ws]),
+            _c_array(ctypes.c_void_p, [f.data_ptr() for f, _ in packs]),
+            _c_array(ctypes.c_void_p, [0 if d is None else d.data_ptr() for _, d in packs])]
+    with torch.cuda.device(dev):
+        _lib.call('sed_conv_pack_weights_multi', len(ws), keep[0][1], keep[1][1], keep[2][1], keep[3][1], keep[4][1],
+                  _lib.stream_of(ws[0]))
+    return packs
+
+
+def conv3x3_wgrad_slabs(dy, x):
+    """The split-K slabs (splits, 9, Cout, Cin) fp32 of dW = dy^T x, not yet folded (see unpack_wgrad_multi)."""
+    assert dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16
+    assert dy.is_contiguous() and x.is_contiguous() and dy.shape[:3] == x.shape[:3]
+    b, h, w, cin = x.shape
+    cout = dy.shape[3]
+    with torch.cuda.device(x.device):
+        splits = _lib.lib().sed_conv3x3_tc_wgrad_splits(b, h, w, cin, cout)
+        slabs = torch.empty((splits, 9, cout, cin), dtype=torch.float32, device=x.device)
+        _lib.call('sed_conv3x3_tc_wgrad', dy.data_ptr(), x.data_ptr(), slabs.data_ptr(), b, h, w, cin,
+                  cout, _lib.stream_of(x))
+    return slabs
+
+
+def unpack_wgrad_multi(items):
+    """[(slabs (S, 9, Cout, Cin) fp32, out (Cout, Cin, 3, 3) fp32)]: fold the split-K slabs of up to 8 layers into their
+    OIHW gradients with ONE launch (sed_conv_unpack_wgrad_multi), on the current stream."""
+    import ctypes
+    if not items:
+        return
+    dev = items[0][0].device
+    keep = [_c_array(ctypes.c_void_p, [s.data_ptr() for s, _ in items]),
+            _c_array(ctypes.c_int, [s.shape[0] for s, _ in items]),
+            _c_array(ctypes.c_int, [s.shape[2] for s, _ in items]), _c_array(ctypes.c_int, [s.shape[3] for s, _ in items]),
+            _c_array(ctypes.c_void_p, [o.data_ptr() for _, o in items])]
+    for s, o in items:
+        assert o.is_contiguous() and o.dtype == torch.float32 and o.numel() == 9 * s.shape[2] * s.shape[3]
+    with torch.cuda.device(dev):
+        _lib.call('sed_conv_unpack_wgrad_multi', len(items), keep[0][1], keep[1][1], keep[2][1], keep[3][1], keep[4][1],
+                  _lib.stream_of(items[0][0]))
+
+
 # CTA-pair (tcgen05.mma.cta_group::2) kernel: measured 33.9 vs 35.7 ms/step (tools/ab_step.py conv.USE_2CTA=0,1)
 USE_2CTA = True
 # Cout = 64: the three kw taps stacked in N (csrc/conv_halo2_kw_tc.cu), A/B switch for tools/ab_step.py.  Used from

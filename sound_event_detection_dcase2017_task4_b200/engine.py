@@ -32,8 +32,9 @@ def _bn_state(partial, count, bn, training):
     return ops.bn_finalize(partial, count, bn) if training else ops.bn_eval_affine(bn)
 
 
-def _conv_layer(conv_mod, bn_mod, x_in, ph, pw, training, out_f32, keep):
-    """conv3x3 -> BN(train: batch stats) -> ReLU -> avgpool(ph, pw)."""
+def _conv_layer(conv_mod, bn_mod, x_in, ph, pw, training, out_f32, keep, packs=None):
+    """conv3x3 -> BN(train: batch stats) -> ReLU -> avgpool(ph, pw).  ``packs``: {conv module: (fwd, dgrad) bf16 weight
+    packs} made for all layers at once (trunk_forward); without it the layer packs its own."""
     lc = LayerCtx()
     lc.conv, lc.bn, lc.ph, lc.pw = conv_mod, bn_mod, ph, pw
     w = conv_mod.weight
@@ -50,7 +51,10 @@ def _conv_layer(conv_mod, bn_mod, x_in, ph, pw, training, out_f32, keep):
             raise NotImplementedError(
                 'tensor-core conv path needs W | 128 (W >= 8), Cin in {64,128k}, Cout in {64,128,256,512}; '
                 'got W=%d Cin=%d Cout=%d' % (wd, cin, cout))
-        wf, lc.wd = tcconv.pack_weights(w, want_fwd=True, want_dgrad=keep)
+        if packs is not None and conv_mod in packs:
+            wf, lc.wd = packs[conv_mod]
+        else:
+            wf, lc.wd = tcconv.pack_weights(w, want_fwd=True, want_dgrad=keep)
         y, partial = tcconv.conv3x3(x_in, wf, cout, want_stats=True)
     st = _bn_state(partial, b * h * wd, bn_mod, training)
     out = ops.bn_relu_pool_fwd(y, st, ph, pw, out_f32=out_f32)
@@ -95,14 +99,17 @@ def trunk_forward(model, wave, lam, training, stripes=None, keep=None):
     ctx.logmel, ctx.st0, ctx.x0 = (logmel, st0, x) if keep else (None, None, None)
     ctx.layers = []
     blocks = (model.conv_block1, model.conv_block2, model.conv_block3, model.conv_block4)
+    # bf16 weight packs of all tensor-core layers in one launch (they were 7 launches of ~10 us)
+    tc_convs = [c for blk in blocks for c in (blk.conv1, blk.conv2) if c.weight.shape[1] > 1]
+    packs = dict(zip(tc_convs, tcconv.pack_weights_multi([c.weight for c in tc_convs], want_dgrad=keep)))
     for bi, blk in enumerate(blocks):
         last = bi == len(blocks) - 1
-        x, lc = _conv_layer(blk.conv1, blk.bn1, x, 1, 1, training, False, keep)
+        x, lc = _conv_layer(blk.conv1, blk.bn1, x, 1, 1, training, False, keep, packs)
         ctx.layers.append(lc)
         wd = x.shape[2]
         # blocks 1-3: avg_pool 2x2; block 4: pool 1x1 then mean over the 8 remaining mel bins
         ph, pw = (1, wd) if last else (2, 2)
-        x, lc = _conv_layer(blk.conv2, blk.bn2, x, ph, pw, training, last, keep)
+        x, lc = _conv_layer(blk.conv2, blk.bn2, x, ph, pw, training, last, keep, packs)
         ctx.layers.append(lc)
     b, tp, one, c = x.shape
     return x.view(b, tp, c), ctx
@@ -154,6 +161,7 @@ def trunk_backward(ctx, dfeat, grad_of, overlap_wgrad=None):
     main, side = _side_stream(dev) if overlap_wgrad else (None, None)
     used_side = False
     held = []
+    side_slabs, main_slabs = [], []
     gy_partial = None
     for li in range(len(ctx.layers) - 1, -1, -1):
         lc = ctx.layers[li]
@@ -187,14 +195,18 @@ def trunk_backward(ctx, dfeat, grad_of, overlap_wgrad=None):
                 held.append((dy, x_in))
                 used_side = True
                 with torch.cuda.stream(side):
-                    tcconv.conv3x3_wgrad(dy, x_in, out=gw)
+                    side_slabs.append((tcconv.conv3x3_wgrad_slabs(dy, x_in), gw))
             elif gw is not None:
-                tcconv.conv3x3_wgrad(dy, x_in, out=gw)
+                main_slabs.append((tcconv.conv3x3_wgrad_slabs(dy, x_in), gw))
         lc.y = lc.x_in = None
     g0w, g0b = grad_of(ctx.bn0.weight), grad_of(ctx.bn0.bias)
     if g0w is not None or g0b is not None:
         ops.bn0_bwd(dA, ctx.logmel, ctx.st0, ctx.bn0, ctx.t_stripes, ctx.f_stripes, ctx.lam, g0w, g0b)
+    # the split-K slabs of all weight gradients are folded into the OIHW gradients by one launch per stream
+    tcconv.unpack_wgrad_multi(main_slabs)
     if used_side:
+        with torch.cuda.stream(side):
+            tcconv.unpack_wgrad_multi(side_slabs)
         done = torch.cuda.Event()
         done.record(side)
         main.wait_event(done)

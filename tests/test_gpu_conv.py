@@ -207,3 +207,27 @@ def test_conv_wgrad_cta_pair_kernel(B, H, W, Cin, Cout):
     finally:
         _lib.lib().sed_conv3x3_tc_wgrad_use_pairs(was)
     assert torch.equal(single, pair)
+
+
+def test_multi_layer_pack_and_unpack_equal_per_layer_entry_points():
+    """sed_conv_pack_weights_multi / sed_conv_unpack_wgrad_multi (one launch for all layers of the model) produce the
+    same bytes as the per-layer entry points."""
+    from sound_event_detection_dcase2017_task4_b200 import conv
+    shapes = [(64, 64), (128, 64), (128, 128), (256, 128), (256, 256), (512, 256), (512, 512)]
+    ws = [(_rand((co, ci, 3, 3), 50 + i) * 0.05).cuda() for i, (co, ci) in enumerate(shapes)]
+    multi = conv.pack_weights_multi(ws, want_dgrad=True)
+    for w, (f, d) in zip(ws, multi):
+        f1, d1 = conv.pack_weights(w)
+        assert torch.equal(f, f1) and torch.equal(d, d1)
+    fwd_only = conv.pack_weights_multi(ws[:3], want_dgrad=False)
+    assert all(d is None for _, d in fwd_only) and torch.equal(fwd_only[2][0], multi[2][0])
+    items, refs = [], []
+    for i, (B, H, W, Cin, Cout) in enumerate([(2, 25, 16, 128, 256), (3, 50, 32, 64, 128), (2, 101, 64, 64, 64),
+                                               (1, 125, 8, 512, 512)]):
+        x = _rand((B, H, W, Cin), 60 + i).cuda().to(torch.bfloat16)
+        dy = _rand((B, H, W, Cout), 70 + i).cuda().to(torch.bfloat16)
+        refs.append(conv.conv3x3_wgrad(dy, x))
+        items.append((conv.conv3x3_wgrad_slabs(dy, x), torch.full((Cout, Cin, 3, 3), 7.0, device='cuda')))
+    conv.unpack_wgrad_multi(items)
+    for (_, out), ref in zip(items, refs):
+        assert torch.equal(out, ref)
