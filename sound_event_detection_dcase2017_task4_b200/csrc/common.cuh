@@ -68,7 +68,23 @@ __device__ __forceinline__ void colsum2_block(const float* __restrict__ a, const
   __shared__ double s_part[2][kColLanes][33];
   double xa = 0.0, xb = 0.0;
   if (ok) {
-    for (int p = threadIdx.y; p < P; p += kColLanes) {
+    // four rows per trip with the loads issued before the (sequential, fixed-order) fp64 adds: the loop is a chain of
+    // L2 round trips otherwise (37 of them for the 592 partial rows of a convolution: 17 us per finalize)
+    int p = threadIdx.y;
+    for (; p + 3 * kColLanes < P; p += 4 * kColLanes) {
+      float va[4], vb[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        va[u] = a[(long long)(p + u * kColLanes) * stride + col];
+        vb[u] = b ? b[(long long)(p + u * kColLanes) * stride + col] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        xa += (double)va[u];
+        xb += (double)vb[u];
+      }
+    }
+    for (; p < P; p += kColLanes) {
       xa += (double)a[(long long)p * stride + col];
       if (b) xb += (double)b[(long long)p * stride + col];
     }
