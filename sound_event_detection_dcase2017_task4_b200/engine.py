@@ -42,7 +42,7 @@ def _conv_layer(conv_mod, bn_mod, x_in, ph, pw, training, out_f32, keep, packs=N
     if cin == 1:
         lc.is_c1 = True
         b, h, wd = x_in.shape
-        y, partial = ops.conv_c1_fwd(x_in, w, want_stats=True)
+        y, partial = ops.conv_c1_fwd(x_in, w, want_stats=True)      # (this kernel always reduces its statistics)
         lc.wd = None
     else:
         lc.is_c1 = False
@@ -55,7 +55,10 @@ def _conv_layer(conv_mod, bn_mod, x_in, ph, pw, training, out_f32, keep, packs=N
             wf, lc.wd = packs[conv_mod]
         else:
             wf, lc.wd = tcconv.pack_weights(w, want_fwd=True, want_dgrad=keep)
-        y, partial = tcconv.conv3x3(x_in, wf, cout, want_stats=True)
+        if training:
+            y, partial = tcconv.conv3x3(x_in, wf, cout, want_stats=True)
+        else:                                   # eval: running statistics, the epilogue skips the batch sums
+            y, partial = tcconv.conv3x3(x_in, wf, cout, want_stats=False), None
     st = _bn_state(partial, b * h * wd, bn_mod, training)
     out = ops.bn_relu_pool_fwd(y, st, ph, pw, out_f32=out_f32)
     if keep:
