@@ -193,6 +193,13 @@ int sed_conv_c1_fwd(const float* x, const float* w, void* y, float* stats_partia
                     sed_stream_t stream);
 int sed_conv_c1_wgrad(const float* x, const void* dy, float* partial, int B, int H, int W, int Cout,
                       sed_stream_t stream);
+/* sed_bn_relu_pool_bwd_apply (flat, bf16 dA) of block1.bn1 FUSED into the weight-gradient pass: y and dA stream in, dY is
+ * formed on chip (same arithmetic, same bf16 rounding), feeds the weight-gradient product and is written to `dy` for
+ * sed_conv_c1_dgrad.  coef = the (3, 64) output of sed_bn_bwd_finalize.  One pass over y and dA replaces the apply
+ * pass plus the weight gradient's own pass over dY. */
+int sed_bn_apply_conv_c1_wgrad(const float* x, const void* y, const void* dA, const float* scale, const float* shift,
+                               const float* mean, const float* invstd, const float* coef, void* dy, float* partial, int B,
+                               int H, int W, int Cout, sed_stream_t stream);
 int sed_conv_c1_dgrad(const void* dy, const float* w, float* dx, int B, int H, int W, int Cout, sed_stream_t stream);
 
 /* ---- heads + loss (pytorch/models.py:118-149, :221-227, :306-312; pytorch/losses.py:5-12) ------ */

@@ -60,6 +60,7 @@ SIGNATURES = {
     'sed_conv_c1_grid': [],
     'sed_conv_c1_fwd': [P, P, P, P, I, I, I, I, P],
     'sed_conv_c1_wgrad': [P, P, P, I, I, I, I, P],
+    'sed_bn_apply_conv_c1_wgrad': [P, P, P, P, P, P, P, P, P, P, I, I, I, I, P],
     'sed_conv_c1_dgrad': [P, P, P, I, I, I, I, P],
     'sed_linear_partials': [],
     'sed_linear_pair_fwd': [P, P, P, I, P, P, I, L, I, P, P, P],

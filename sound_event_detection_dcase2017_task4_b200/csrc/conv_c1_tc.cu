@@ -189,15 +189,26 @@ struct C1WgParams {
   int chunks, items;                  // row chunks per clip, B * chunks
   const float* x0;                    // (B, H, W) fp32
   float* partial;                     // [gridDim.x][64 * 9]
+  // fused BatchNorm-backward apply (kFused): dY is made here from y and dA and also written out for the data gradient
+  const float* scale; const float* shift; const float* mean; const float* invstd; const float* coef;   // (64,) ... (3, 64)
+  __nv_bfloat16* dy_out;              // (B, H, W, 64)
 };
 
+// kFused: the A slabs arriving by TMA are the raw conv output y (tmap_dy) and the incoming gradient dA (tmap_g) of
+// block1.bn1; the builder group that makes a block's im2col tile first turns the two slabs IN PLACE into the dY slab
+// (sed_bn_relu_pool_bwd_apply's arithmetic: element i of both slabs is the same (pixel, channel) whatever the swizzle, and
+// a thread's 16-byte chunks all hold the same 8 channels, whose constants it keeps in registers) and stores it to global
+// memory for the data-gradient kernel.  One pass over y and dA replaces the apply pass plus this kernel's own pass over dY.
+template <bool kFused>
 __global__ void __launch_bounds__(kC1Threads, 1)
-conv_c1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const C1WgParams p) {
+conv_c1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_g,
+                        const C1WgParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;                                          // kWgStages x 16 KB   dY slabs (TMA)
   uint8_t* smem_b = smem + kWgStages * 16384;                      // kWgStages x 16 KB   im2col tiles (built here)
-  float* sx = reinterpret_cast<float*>(smem_b + kWgStages * 16384);   // [kWgRows + 2][W + 2] fp32 input rows
+  uint8_t* smem_g = smem_b + kWgStages * 16384;                    // kFused: kWgStages x 16 KB   dA slabs (TMA)
+  float* sx = reinterpret_cast<float*>(smem_g + (kFused ? kWgStages * 16384 : 0));   // [kWgRows + 2][W + 2] fp32 input rows
   __shared__ uint64_t a_full[kWgStages], b_full[kWgStages], empty_bar[kWgStages], done_bar;
   __shared__ uint32_t tmem_base_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -206,6 +217,7 @@ conv_c1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const C1WgP
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmap_dy);
+    if (kFused) tma_prefetch_desc(&tmap_g);
     for (int s = 0; s < kWgStages; ++s) {
       mbar_init(&a_full[s], 1);
       mbar_init(&b_full[s], 128);
@@ -229,8 +241,9 @@ conv_c1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const C1WgP
         const int nkb = (min(kWgRows, p.H - h0) + p.bh - 1) / p.bh;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[st], ph ^ 1);
-          mbar_arrive_expect_tx(&a_full[st], 16384u);
+          mbar_arrive_expect_tx(&a_full[st], kFused ? 32768u : 16384u);
           tma_load_4d(smem_a + st * 16384, &tmap_dy, &a_full[st], 0, 0, h0 + kb * p.bh, b);   // rows >= H: zeros
+          if (kFused) tma_load_4d(smem_g + st * 16384, &tmap_g, &a_full[st], 0, 0, h0 + kb * p.bh, b);
           if (++st == kWgStages) { st = 0; ph ^= 1; }
         }
       }
@@ -283,6 +296,21 @@ conv_c1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const C1WgP
         pf[q] = (r < kWgRows + 2 && h >= 0 && h < p.H && w >= 0 && w < p.W) ? __ldg(img + (long long)h * p.W + w) : 0.f;
       }
     };
+    // kFused: the 8 channels of this thread's 16-byte chunks (logical chunk = physical chunk ^ (row & 7); a thread's
+    // chunks are 16 rows apart, so the logical chunk is the same for all of them) and their apply constants
+    const int lc = (gt & 7) ^ ((gt >> 3) & 7);
+    float k_sc[8], k_sh[8], k_a[8], k_b[8], k_c[8];
+    if (kFused) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = lc * 8 + e;
+        const float a = p.coef[c], c2 = p.coef[64 + c], c3 = p.coef[128 + c];
+        k_sc[e] = p.scale[c]; k_sh[e] = p.shift[c];
+        k_a[e] = a;
+        k_b[e] = -a * c3 * p.invstd[c];
+        k_c[e] = -a * c2 - k_b[e] * p.mean[c];
+      }
+    }
     int cur = 0;
     if ((int)blockIdx.x < p.items) fetch(blockIdx.x);
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
@@ -304,6 +332,35 @@ conv_c1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const C1WgP
           const int st = nblk % kWgStages;
           const uint32_t ph = (uint32_t)(nblk / kWgStages) & 1u;
           mbar_wait(&empty_bar[st], ph ^ 1);
+          if (kFused) {
+            mbar_wait(&a_full[st], ph);                            // y and dA slabs of this block have landed
+            uint4* ys = reinterpret_cast<uint4*>(smem_a + st * 16384);
+            const uint4* gs = reinterpret_cast<const uint4*>(smem_g + st * 16384);
+            const int bimg = item / p.chunks;
+#pragma unroll 2
+            for (int k = 0; k < 8; ++k) {
+              const int i = gt + 128 * k;                          // chunk index: slab row i >> 3 (pixel), chunk i & 7
+              const int prow = i >> 3;
+              const int hh = h0 + kb * p.bh + prow / p.W, ww = prow % p.W;
+              const uint4 yv = ys[i], gv = gs[i];
+              const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
+              uint32_t ow[4];
+#pragma unroll
+              for (int e2 = 0; e2 < 4; ++e2) {
+                const float2 xf = unpack_bf16x2(yw[e2]), gf = unpack_bf16x2(gw[e2]);
+                const float g0 = fmaf(xf.x, k_sc[2 * e2], k_sh[2 * e2]) > 0.f ? gf.x : 0.f;
+                const float g1 = fmaf(xf.y, k_sc[2 * e2 + 1], k_sh[2 * e2 + 1]) > 0.f ? gf.y : 0.f;
+                const float o0 = fmaf(k_a[2 * e2], g0, fmaf(k_b[2 * e2], xf.x, k_c[2 * e2]));
+                const float o1 = fmaf(k_a[2 * e2 + 1], g1, fmaf(k_b[2 * e2 + 1], xf.y, k_c[2 * e2 + 1]));
+                ow[e2] = pack_bf16x2(o0, o1);
+              }
+              const bool ok = hh < p.H;                            // rows beyond the image: dY = 0 (what TMA's zero fill gave)
+              const uint4 ov = ok ? make_uint4(ow[0], ow[1], ow[2], ow[3]) : make_uint4(0u, 0u, 0u, 0u);
+              ys[i] = ov;
+              if (ok)
+                *reinterpret_cast<uint4*>(p.dy_out + (((long long)bimg * p.H + hh) * p.W + ww) * 64 + lc * 8) = ov;
+            }
+          }
           uint8_t* tile = smem_b + st * 16384;
           const int r = kb * p.bh + gt / p.W, wq = gt % p.W;       // pixel row within the item, column
           const float* c = sxc + r * ldx + wq;                     // window top-left (staged row r <-> image row h0+r-1)
@@ -399,30 +456,58 @@ int sed_conv_c1_dgrad(const void* dy, const float* w, float* dx, int B, int H, i
   return 0;
 }
 
+namespace {
+int launch_c1_wgrad(const char* name, const float* x, const void* a_src, const void* g_src, C1WgParams p, int B, int H, int W,
+                    cudaStream_t stream) {
+  SED_REQUIRE(W >= 16 && W <= 128 && 128 % W == 0, "%s: W=%d must divide 128 and be >= 16", name, W);
+  SED_REQUIRE(B >= 1 && H >= 1 && (long long)B * H < (1LL << 31), "%s: bad shape", name);
+  p.B = B; p.H = H; p.W = W; p.bh = 128 / W;
+  p.chunks = (H + kWgRows - 1) / kWgRows;
+  p.items = B * p.chunks;
+  p.x0 = x;
+  const bool fused = g_src != nullptr;
+  alignas(64) CUtensorMap tm, tg;
+  const uint64_t dims[4] = {64, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  const uint64_t strides[3] = {128, (uint64_t)W * 128, (uint64_t)H * W * 128};
+  const uint32_t box[4] = {64, (uint32_t)W, (uint32_t)p.bh, 1};
+  if (int rc = tc::make_tmap_bf16(&tm, a_src, 4, dims, strides, box, "conv_c1 wgrad dY / y map")) return rc;
+  if (int rc = tc::make_tmap_bf16(&tg, fused ? g_src : a_src, 4, dims, strides, box, "conv_c1 wgrad dA map")) return rc;
+  const size_t smem = (size_t)(fused ? 3 : 2) * kWgStages * 16384 + (size_t)2 * kWgSxFloats * sizeof(float) + 1024;
+  SED_REQUIRE(smem <= 227 * 1024, "%s: shared memory", name);
+  // every one of the sed_conv_c1_grid() partial rows is written (CTAs without work write zeros)
+  if (fused) {
+    SED_CUDA(cudaFuncSetAttribute(conv_c1_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_c1_wgrad_tc_kernel<true><<<sed_conv_c1_grid(), kC1Threads, smem, stream>>>(tm, tg, p);
+  } else {
+    SED_CUDA(cudaFuncSetAttribute(conv_c1_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_c1_wgrad_tc_kernel<false><<<sed_conv_c1_grid(), kC1Threads, smem, stream>>>(tm, tg, p);
+  }
+  SED_LAUNCH_CHECK("conv_c1_wgrad_tc_kernel");
+  return 0;
+}
+}  // namespace
+
 int sed_conv_c1_wgrad(const float* x, const void* dy, float* partial, int B, int H, int W, int Cout,
                       sed_stream_t stream) {
   SED_REQUIRE(x && dy && partial, "sed_conv_c1_wgrad: null pointer");
   SED_REQUIRE(Cout == 64, "sed_conv_c1_wgrad: Cout=%d unsupported (the tensor-core path is built for 64)", Cout);
-  SED_REQUIRE(W >= 16 && W <= 128 && 128 % W == 0, "sed_conv_c1_wgrad: W=%d must divide 128 and be >= 16", W);
-  SED_REQUIRE(B >= 1 && H >= 1 && (long long)B * H < (1LL << 31), "sed_conv_c1_wgrad: bad shape");
-  C1WgParams p;
-  p.B = B; p.H = H; p.W = W; p.bh = 128 / W;
-  p.chunks = (H + kWgRows - 1) / kWgRows;
-  p.items = B * p.chunks;
-  p.x0 = x; p.partial = partial;
-  alignas(64) CUtensorMap tm;
-  {
-    const uint64_t dims[4] = {64, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-    const uint64_t strides[3] = {128, (uint64_t)W * 128, (uint64_t)H * W * 128};
-    const uint32_t box[4] = {64, (uint32_t)W, (uint32_t)p.bh, 1};
-    if (int rc = tc::make_tmap_bf16(&tm, dy, 4, dims, strides, box, "conv_c1 wgrad dY map")) return rc;
-  }
-  const size_t smem = (size_t)2 * kWgStages * 16384 + (size_t)2 * kWgSxFloats * sizeof(float) + 1024;
-  SED_CUDA(cudaFuncSetAttribute(conv_c1_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // every one of the sed_conv_c1_grid() partial rows is written (CTAs without work write zeros)
-  conv_c1_wgrad_tc_kernel<<<sed_conv_c1_grid(), kC1Threads, smem, (cudaStream_t)stream>>>(tm, p);
-  SED_LAUNCH_CHECK("conv_c1_wgrad_tc_kernel");
-  return 0;
+  C1WgParams p{};
+  p.partial = partial;
+  return launch_c1_wgrad("sed_conv_c1_wgrad", x, dy, nullptr, p, B, H, W, (cudaStream_t)stream);
+}
+
+int sed_bn_apply_conv_c1_wgrad(const float* x, const void* y, const void* dA, const float* scale, const float* shift,
+                               const float* mean, const float* invstd, const float* coef, void* dy, float* partial, int B,
+                               int H, int W, int Cout, sed_stream_t stream) {
+  SED_REQUIRE(x && y && dA && scale && shift && mean && invstd && coef && dy && partial,
+              "sed_bn_apply_conv_c1_wgrad: null pointer");
+  SED_REQUIRE(Cout == 64, "sed_bn_apply_conv_c1_wgrad: Cout=%d unsupported (the tensor-core path is built for 64)", Cout);
+  SED_REQUIRE(aligned(dy, 16), "sed_bn_apply_conv_c1_wgrad: dy must be 16-byte aligned");
+  C1WgParams p{};
+  p.partial = partial;
+  p.scale = scale; p.shift = shift; p.mean = mean; p.invstd = invstd; p.coef = coef;
+  p.dy_out = reinterpret_cast<__nv_bfloat16*>(dy);
+  return launch_c1_wgrad("sed_bn_apply_conv_c1_wgrad", x, y, dA, p, B, H, W, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -135,6 +135,8 @@ OVERLAP_LAYERS = frozenset((1, 2, 3, 4, 5, 6, 7))
 # dedicated 24-warp/SM reduction kernels stream at ~5 TB/s, and the epilogue is already the critical path of the
 # K = 576 layers.  Off.
 FUSE_BN_REDUCE = False
+# Layer 1 (Cin = 1): BatchNorm-backward apply fused into the weight-gradient kernel (sed_bn_apply_conv_c1_wgrad).
+FUSE_C1_APPLY = True
 
 
 def _side_stream(device):
@@ -168,17 +170,25 @@ def trunk_backward(ctx, dfeat, grad_of, overlap_wgrad=None):
     gy_partial = None
     for li in range(len(ctx.layers) - 1, -1, -1):
         lc = ctx.layers[li]
-        dy = ops.bn_relu_pool_bwd(lc.y, dA, lc.st, lc.bn, lc.ph, lc.pw, grad_of(lc.bn.weight),
-                                  grad_of(lc.bn.bias), gy_partial=gy_partial, frozen=not ctx.training)
-        gy_partial = None
         gw = grad_of(lc.conv.weight)
+        fuse_c1 = (FUSE_C1_APPLY and lc.is_c1 and gw is not None and dA.dtype == torch.bfloat16
+                   and (lc.ph, lc.pw) == (1, 1) and lc.y.shape[3] == 64 and lc.y.shape[2] >= 16)
+        if fuse_c1:
+            # layer 1: the apply pass runs inside the weight-gradient kernel (one pass over y and dA instead of two)
+            coef = ops.bn_bwd_coef(lc.y, dA, lc.st, lc.bn, lc.ph, lc.pw, grad_of(lc.bn.weight), grad_of(lc.bn.bias),
+                                   frozen=not ctx.training)
+            dy = ops.bn_apply_conv_c1_wgrad(lc.x_in, lc.y, dA, lc.st, coef, gw)
+        else:
+            dy = ops.bn_relu_pool_bwd(lc.y, dA, lc.st, lc.bn, lc.ph, lc.pw, grad_of(lc.bn.weight),
+                                      grad_of(lc.bn.bias), gy_partial=gy_partial, frozen=not ctx.training)
+        gy_partial = None
         side_wgrad = overlap_wgrad and gw is not None and not lc.is_c1 and li in OVERLAP_LAYERS
         if side_wgrad:
             ready = torch.cuda.Event()
             ready.record(main)
         x_in = lc.x_in
         if lc.is_c1:
-            if gw is not None:
+            if gw is not None and not fuse_c1:
                 ops.conv_c1_wgrad(x_in, dy, gw)
             dA = ops.conv_c1_dgrad(dy, lc.conv.weight)                 # (B, T, M) fp32
         else:

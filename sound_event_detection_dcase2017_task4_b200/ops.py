@@ -79,13 +79,9 @@ def sched_words(t):
     return w
 
 
-def bn_relu_pool_bwd(y, dA, st, bn, ph, pw, dgamma, dbeta, gy_partial=None, frozen=False):
-    """Two-pass BN+ReLU+pool backward.  Writes bn parameter grads into dgamma/dbeta (fp32 (C,)
-    tensors, may be None) and returns dY (bf16, same shape as y).
-
-    ``gy_partial``: (P, 2, C) partial sums of g and g*y already produced by the data-gradient kernel that wrote
-    ``dA`` (conv.conv3x3_dgrad_bnr); the reduction pass over y and dA is then skipped.
-    ``frozen``: ``st`` holds running statistics (eval-mode forward): they are constants, dY = gamma * invstd * g."""
+def bn_bwd_coef(y, dA, st, bn, ph, pw, dgamma, dbeta, gy_partial=None, frozen=False):
+    """First half of the BN+ReLU+pool backward: the reduction pass over (y, dA) and the finalize kernel.  Writes the bn
+    parameter grads into dgamma / dbeta (may be None) and returns the (3, C) coefficient rows of the apply pass."""
     b, h, w, c = y.shape
     f32 = 1 if dA.dtype == F32 else 0
     with _dev(y):
@@ -102,10 +98,45 @@ def bn_relu_pool_bwd(y, dA, st, bn, ph, pw, dgamma, dbeta, gy_partial=None, froz
         call('sed_bn_bwd_finalize', partial.data_ptr(), P, c, float(b * h * w), ptr(bn.weight),
              st.invstd.data_ptr(), st.mean.data_ptr(), ptr(dgamma), ptr(dbeta), 0, 1 if frozen else 0,
              coef.data_ptr(), s)
+    return coef
+
+
+def bn_bwd_apply(y, dA, st, coef, ph, pw):
+    """Second half: dY (bf16, same shape as y) from y, dA and the coefficient rows."""
+    b, h, w, c = y.shape
+    f32 = 1 if dA.dtype == F32 else 0
+    with _dev(y):
         dy = _empty(y.shape, BF16, y)
         call('sed_bn_relu_pool_bwd_apply', y.data_ptr(), dA.data_ptr(), f32, st.scale.data_ptr(),
              st.shift.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(), coef.data_ptr(), b, h, w, c,
-             ph, pw, dy.data_ptr(), sched.data_ptr(), s)
+             ph, pw, dy.data_ptr(), sched_words(y).data_ptr(), stream_of(y))
+    return dy
+
+
+def bn_relu_pool_bwd(y, dA, st, bn, ph, pw, dgamma, dbeta, gy_partial=None, frozen=False):
+    """Two-pass BN+ReLU+pool backward.  Writes bn parameter grads into dgamma/dbeta (fp32 (C,)
+    tensors, may be None) and returns dY (bf16, same shape as y).
+
+    ``gy_partial``: (P, 2, C) partial sums of g and g*y already produced by the data-gradient kernel that wrote
+    ``dA`` (conv.conv3x3_dgrad_bnr); the reduction pass over y and dA is then skipped.
+    ``frozen``: ``st`` holds running statistics (eval-mode forward): they are constants, dY = gamma * invstd * g."""
+    coef = bn_bwd_coef(y, dA, st, bn, ph, pw, dgamma, dbeta, gy_partial=gy_partial, frozen=frozen)
+    return bn_bwd_apply(y, dA, st, coef, ph, pw)
+
+
+def bn_apply_conv_c1_wgrad(x0, y, dA, st, coef, out):
+    """The apply pass of block1.bn1's backward fused into the Cin = 1 weight-gradient kernel: returns dY (bf16, for the
+    data gradient) and writes dW into ``out`` (Cout, 1, 3, 3).  y, dA: (B, H, W, 64) bf16; x0: (B, H, W) fp32."""
+    b, h, wd = x0.shape
+    cout = y.shape[3]
+    assert dA.dtype == BF16 and y.dtype == BF16 and dA.shape == y.shape
+    with _dev(x0):
+        dy = _empty(y.shape, BF16, y)
+        partial = _empty((_lib.lib().sed_conv_c1_grid(), cout * 9), F32, x0)
+        call('sed_bn_apply_conv_c1_wgrad', x0.data_ptr(), y.data_ptr(), dA.data_ptr(), st.scale.data_ptr(),
+             st.shift.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(), coef.data_ptr(), dy.data_ptr(),
+             partial.data_ptr(), b, h, wd, cout, stream_of(x0))
+    reduce_partials(partial, out)
     return dy
 
 
