@@ -38,6 +38,14 @@ struct C1Params {
   float* dx;         // (B, H, W)
 };
 
+// packed fp32 pair FMA (one issue slot for two IEEE fmas: the fused apply transform is issue-bound)
+__device__ __forceinline__ float2 c1_fma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                     rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+
 __device__ __forceinline__ int sw128_off(int row, int col_bf16) {
   const int chunk = (col_bf16 * 2) >> 4, within = (col_bf16 * 2) & 15;
   return row * 128 + ((chunk ^ (row & 7)) << 4) + within;
@@ -299,16 +307,16 @@ conv_c1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __gri
     // kFused: the 8 channels of this thread's 16-byte chunks (logical chunk = physical chunk ^ (row & 7); a thread's
     // chunks are 16 rows apart, so the logical chunk is the same for all of them) and their apply constants
     const int lc = (gt & 7) ^ ((gt >> 3) & 7);
-    float k_sc[8], k_sh[8], k_a[8], k_b[8], k_c[8];
+    float2 k_sc[4], k_sh[4], k_a[4], k_b[4], k_c[4];               // channel pairs (2 e2, 2 e2 + 1) of the chunk
     if (kFused) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int c = lc * 8 + e;
         const float a = p.coef[c], c2 = p.coef[64 + c], c3 = p.coef[128 + c];
-        k_sc[e] = p.scale[c]; k_sh[e] = p.shift[c];
-        k_a[e] = a;
-        k_b[e] = -a * c3 * p.invstd[c];
-        k_c[e] = -a * c2 - k_b[e] * p.mean[c];
+        const float kb = -a * c3 * p.invstd[c];
+        const float kc = -a * c2 - kb * p.mean[c];
+        if (e & 1) { k_sc[e >> 1].y = p.scale[c]; k_sh[e >> 1].y = p.shift[c]; k_a[e >> 1].y = a; k_b[e >> 1].y = kb; k_c[e >> 1].y = kc; }
+        else { k_sc[e >> 1].x = p.scale[c]; k_sh[e >> 1].x = p.shift[c]; k_a[e >> 1].x = a; k_b[e >> 1].x = kb; k_c[e >> 1].x = kc; }
       }
     }
     int cur = 0;
@@ -337,7 +345,7 @@ conv_c1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __gri
             uint4* ys = reinterpret_cast<uint4*>(smem_a + st * 16384);
             const uint4* gs = reinterpret_cast<const uint4*>(smem_g + st * 16384);
             const int bimg = item / p.chunks;
-#pragma unroll 2
+#pragma unroll
             for (int k = 0; k < 8; ++k) {
               const int i = gt + 128 * k;                          // chunk index: slab row i >> 3 (pixel), chunk i & 7
               const int prow = i >> 3;
@@ -348,11 +356,10 @@ conv_c1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __gri
 #pragma unroll
               for (int e2 = 0; e2 < 4; ++e2) {
                 const float2 xf = unpack_bf16x2(yw[e2]), gf = unpack_bf16x2(gw[e2]);
-                const float g0 = fmaf(xf.x, k_sc[2 * e2], k_sh[2 * e2]) > 0.f ? gf.x : 0.f;
-                const float g1 = fmaf(xf.y, k_sc[2 * e2 + 1], k_sh[2 * e2 + 1]) > 0.f ? gf.y : 0.f;
-                const float o0 = fmaf(k_a[2 * e2], g0, fmaf(k_b[2 * e2], xf.x, k_c[2 * e2]));
-                const float o1 = fmaf(k_a[2 * e2 + 1], g1, fmaf(k_b[2 * e2 + 1], xf.y, k_c[2 * e2 + 1]));
-                ow[e2] = pack_bf16x2(o0, o1);
+                const float2 act = c1_fma2(xf, k_sc[e2], k_sh[e2]);                  // bn(y): the ReLU mask
+                const float2 gm = make_float2(act.x > 0.f ? gf.x : 0.f, act.y > 0.f ? gf.y : 0.f);
+                const float2 o = c1_fma2(k_a[e2], gm, c1_fma2(k_b[e2], xf, k_c[e2]));
+                ow[e2] = pack_bf16x2(o.x, o.y);
               }
               const bool ok = hh < p.H;                            // rows beyond the image: dY = 0 (what TMA's zero fill gave)
               const uint4 ov = ok ? make_uint4(ow[0], ow[1], ow[2], ow[3]) : make_uint4(0u, 0u, 0u, 0u);
