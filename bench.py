@@ -592,6 +592,7 @@ def run_ours(args):
                 'bound': 'tensor', 'achieved': round(achieved, 2), 'peak': peaks['bf16_sustained'],
                 'unit': 'TFLOP/s', 'frac': round(achieved / peaks['bf16_sustained'], 4),
                 'peak_source': peaks['source'] + ' bf16_tflops_sustained (kernel timed inside a long step)',
+                'peak_burst': peaks['bf16_burst'], 'frac_of_burst': round(achieved / peaks['bf16_burst'], 4),
                 'launches_per_step': n_conv, 'avg_launch_ms': round(conv_ms / n_conv, 4),
                 'flop_per_launch_avg': flops_step / n_conv, 'traffic': conv_traffic(),
                 'share_of_step': round(conv_ms / total_ms, 4),
